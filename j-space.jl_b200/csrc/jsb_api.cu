@@ -1,0 +1,839 @@
+// jsb_api.cu — host side of libjspace_b200.so: the C ABI of include/jspace_b200.h.
+//
+// Graph construction and seeding rules (src/J_Space.jl:43-163), parameter validation, device
+// workspace/outputs, the kernel launch, and re-materialisation of the reference's outputs
+// (event log `df`, clone table set_mut_pop/α, final lattice, ordered lists).
+// There is no CPU simulation path in this library.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "jsb_device.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      int _c = (_e == cudaErrorMemoryAllocation) ? JSB_ENOMEM : JSB_ECUDA;                    \
+      rc = fail(_c, "%s failed: %s", #expr, cudaGetErrorString(_e));                          \
+      goto done;                                                                              \
+    }                                                                                         \
+  } while (0)
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Graph
+// ------------------------------------------------------------------------------------------------
+struct jsb_graph {
+  int kind = 0;  // 0 lattice, 1 csr
+  uint32_t n1 = 0, n2 = 0, n3 = 0;
+  int64_t nv = 0, ne = 0;
+  int64_t lattice_row = 0, lattice_col = 0;
+  std::vector<uint32_t> rowptr, colidx;  // csr, 0-based
+  bool have_cand = false;
+  std::vector<int64_t> cand;  // 1-based
+  // device copies (one device at a time; re-uploaded when the device changes)
+  int dev = -1;
+  uint32_t *d_rowptr = nullptr, *d_colidx = nullptr, *d_cand = nullptr;
+  uint32_t d_ncand = 0;
+  bool d_cand_valid = false;
+
+  void drop_device() {
+    if (dev >= 0) {
+      int cur = 0;
+      cudaGetDevice(&cur);
+      cudaSetDevice(dev);
+      cudaFree(d_rowptr);
+      cudaFree(d_colidx);
+      cudaFree(d_cand);
+      cudaSetDevice(cur);
+    }
+    d_rowptr = d_colidx = d_cand = nullptr;
+    dev = -1;
+    d_cand_valid = false;
+  }
+};
+
+namespace {
+
+// neighbours of 0-based vertex v, ascending, into out[]; returns degree
+int host_neighbors(const jsb_graph& g, uint32_t v, uint32_t* out, int cap) {
+  if (g.kind == 0) {
+    uint32_t x = v % g.n1, yz = v / g.n1, y = yz % g.n2, z = yz / g.n2;
+    uint32_t plane = g.n1 * g.n2;
+    int d = 0;
+    auto put = [&](uint32_t w) { if (d < cap) out[d] = w; ++d; };
+    if (z > 0) put(v - plane);
+    if (y > 0) put(v - g.n1);
+    if (x > 0) put(v - 1);
+    if (x + 1 < g.n1) put(v + 1);
+    if (y + 1 < g.n2) put(v + g.n1);
+    if (z + 1 < g.n3) put(v + plane);
+    return d;
+  }
+  uint32_t a = g.rowptr[v], b = g.rowptr[v + 1];
+  for (uint32_t e = a; e < b; ++e)
+    if ((int)(e - a) < cap) out[e - a] = g.colidx[e];
+  return (int)(b - a);
+}
+
+// Graphs.closeness_centrality(g) (normalize = true) and the argmax set, src/J_Space.jl:83-85.
+// One BFS per vertex, vertices split over host threads.
+void closeness_argmax(const jsb_graph& g, std::vector<int64_t>& out) {
+  const int64_t nv = g.nv;
+  std::vector<double> c((size_t)nv, 0.0);
+  unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+  if (nv < 256) nthreads = 1;
+  std::atomic<int64_t> next{0};
+  auto worker = [&]() {
+    std::vector<int32_t> dist((size_t)nv), queue((size_t)nv);
+    uint32_t nb[64];
+    std::vector<uint32_t> big;
+    for (;;) {
+      int64_t u = next.fetch_add(1);
+      if (u >= nv) break;
+      std::fill(dist.begin(), dist.end(), -1);
+      int64_t head = 0, tail = 0, reached = 0;
+      double sigma = 0.0;
+      queue[tail++] = (int32_t)u;
+      dist[u] = 0;
+      while (head < tail) {
+        int32_t v = queue[head++];
+        ++reached;
+        sigma += (double)dist[v];
+        const uint32_t* p = nb;
+        int d = host_neighbors(g, (uint32_t)v, nb, 64);
+        if (d > 64) {
+          big.resize(d);
+          host_neighbors(g, (uint32_t)v, big.data(), d);
+          p = big.data();
+        }
+        for (int i = 0; i < d; ++i) {
+          uint32_t w = p[i];
+          if (dist[w] < 0) { dist[w] = dist[v] + 1; queue[tail++] = (int32_t)w; }
+        }
+      }
+      double l = (double)(reached - 1);
+      if (sigma > 0) {
+        double cu = l / sigma;
+        cu *= l / (double)(nv - 1);
+        c[u] = cu;
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (unsigned i = 1; i < nthreads; ++i) th.emplace_back(worker);
+  worker();
+  for (auto& t : th) t.join();
+  double best = c[0];
+  for (int64_t u = 1; u < nv; ++u) best = std::max(best, c[u]);
+  out.clear();
+  for (int64_t u = 0; u < nv; ++u)
+    if (c[u] == best) out.push_back(u + 1);
+}
+
+int finish_csr(jsb_graph* g, int64_t nv, const std::vector<std::vector<uint32_t>>* adj, const int64_t* rowptr,
+               const int32_t* colidx) {
+  if (nv < 1 || nv >= (int64_t(1) << 28)) return fail(JSB_ECAPACITY, "graph has %lld vertices; supported: 1..2^28-1", (long long)nv);
+  g->kind = 1;
+  g->nv = nv;
+  g->rowptr.assign((size_t)nv + 1, 0);
+  if (adj) {
+    for (int64_t v = 0; v < nv; ++v) g->rowptr[v + 1] = g->rowptr[v] + (uint32_t)(*adj)[v].size();
+    g->colidx.reserve(g->rowptr[nv]);
+    for (int64_t v = 0; v < nv; ++v) g->colidx.insert(g->colidx.end(), (*adj)[v].begin(), (*adj)[v].end());
+  } else {
+    if (rowptr[0] != 0) return fail(JSB_EINVAL, "rowptr[0] must be 0");
+    for (int64_t v = 0; v < nv; ++v) {
+      if (rowptr[v + 1] < rowptr[v]) return fail(JSB_EINVAL, "rowptr is not non-decreasing at vertex %lld", (long long)v + 1);
+      if (rowptr[v + 1] > 0xFFFFFFF0ll) return fail(JSB_ECAPACITY, "too many edges");
+      g->rowptr[v + 1] = (uint32_t)rowptr[v + 1];
+    }
+    g->colidx.resize(g->rowptr[nv]);
+    for (int64_t v = 0; v < nv; ++v) {
+      int64_t prev = 0;
+      for (int64_t e = rowptr[v]; e < rowptr[v + 1]; ++e) {
+        int64_t w = colidx[e];
+        if (w < 1 || w > nv) return fail(JSB_EINVAL, "colidx[%lld] = %lld is outside 1..nv", (long long)e, (long long)w);
+        if (w == v + 1) return fail(JSB_EINVAL, "self-loop at vertex %lld is not supported", (long long)w);
+        if (w <= prev) return fail(JSB_EINVAL, "neighbours of vertex %lld are not strictly ascending", (long long)v + 1);
+        prev = w;
+        g->colidx[e] = (uint32_t)(w - 1);
+      }
+    }
+  }
+  g->ne = (int64_t)g->colidx.size() / 2;
+  return JSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jsb_abi_version(void) { return JSB_ABI_VERSION; }
+
+int jsb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* jsb_last_error(void) { return g_err.c_str(); }
+
+int jsb_graph_lattice(int dim, int64_t row, int64_t col, jsb_graph** out) {
+  if (!out) return fail(JSB_EINVAL, "out is null");
+  *out = nullptr;
+  if (row < 1 || col < 1) return fail(JSB_EINVAL, "row and col must be >= 1 (got %lld, %lld)", (long long)row, (long long)col);
+  if ((double)row * (double)col >= 268435456.0) return fail(JSB_ECAPACITY, "lattice has more than 2^28-1 sites");
+  jsb_graph* g = new (std::nothrow) jsb_graph();
+  if (!g) return fail(JSB_ENOMEM, "out of host memory");
+  g->kind = 0;
+  g->lattice_row = row;
+  g->lattice_col = col;
+  if (dim == 2) {  // Graphs.grid((row, col, 1)) src/J_Space.jl:54
+    g->n1 = (uint32_t)row; g->n2 = (uint32_t)col; g->n3 = 1;
+  } else {         // dim == 3, and the "dim not correct, it set 3" branch :50-51 / :58-59
+    int64_t d = (int64_t)std::trunc(std::pow((double)(row * col), 1.0 / 3.0)) + 1;
+    if ((double)d * d * d >= 268435456.0) { delete g; return fail(JSB_ECAPACITY, "lattice has more than 2^28-1 sites"); }
+    g->n1 = g->n2 = g->n3 = (uint32_t)d;
+  }
+  g->nv = (int64_t)g->n1 * g->n2 * g->n3;
+  g->ne = (int64_t)(g->n1 - 1) * g->n2 * g->n3 + (int64_t)g->n1 * (g->n2 - 1) * g->n3 + (int64_t)g->n1 * g->n2 * (g->n3 - 1);
+  // seed vertex, src/J_Space.jl:131-133 (uses the row/col arguments even for dim 3)
+  double r = (double)row, c = (double)col;
+  double v = (g->nv % 2 == 0) ? (c * std::floor(r / 2.0)) + (std::floor(c / 2.0) + 1.0) : std::floor((double)g->nv / 2.0) + 1.0;
+  int64_t v0 = (int64_t)v;
+  if ((double)v0 == v && v0 >= 1 && v0 <= g->nv) g->cand.push_back(v0);
+  g->have_cand = true;
+  *out = g;
+  return JSB_OK;
+}
+
+int jsb_graph_csr(int64_t nv, const int64_t* rowptr, const int32_t* colidx, jsb_graph** out) {
+  if (!out) return fail(JSB_EINVAL, "out is null");
+  *out = nullptr;
+  if (!rowptr || (!colidx && nv > 0 && rowptr[nv] > 0)) return fail(JSB_EINVAL, "rowptr/colidx is null");
+  jsb_graph* g = new (std::nothrow) jsb_graph();
+  if (!g) return fail(JSB_ENOMEM, "out of host memory");
+  int rc = finish_csr(g, nv, nullptr, rowptr, colidx);
+  if (rc != JSB_OK) { delete g; return rc; }
+  *out = g;
+  return JSB_OK;
+}
+
+int jsb_graph_dense_file(const char* path, jsb_graph** out) {
+  if (!out) return fail(JSB_EINVAL, "out is null");
+  *out = nullptr;
+  if (!path) return fail(JSB_EINVAL, "path is null");
+  FILE* f = std::fopen(path, "r");
+  if (!f) return fail(JSB_EIO, "cannot open adjacency matrix '%s'", path);
+  std::vector<long long> vals;
+  long long x;
+  int got;
+  while ((got = std::fscanf(f, "%lld", &x)) == 1) vals.push_back(x);
+  bool trailing = (got != EOF);
+  std::fclose(f);
+  if (trailing) return fail(JSB_EINVAL, "'%s': non-integer token in adjacency matrix", path);
+  int64_t n = (int64_t)std::llround(std::sqrt((double)vals.size()));
+  if (n < 1 || n * n != (int64_t)vals.size()) return fail(JSB_EINVAL, "'%s': %zu entries do not form a square matrix", path, vals.size());
+  std::vector<std::vector<uint32_t>> adj((size_t)n);
+  for (int64_t i = 0; i < n; ++i)
+    for (int64_t j = 0; j < n; ++j) {
+      bool a = vals[i * n + j] != 0, b = vals[j * n + i] != 0;
+      if (a != b) return fail(JSB_EINVAL, "'%s': adjacency matrix is not symmetric at (%lld,%lld)", path, (long long)i + 1, (long long)j + 1);
+      if (a && i == j) return fail(JSB_EINVAL, "'%s': self-loop at vertex %lld is not supported", path, (long long)i + 1);
+      if (a) adj[i].push_back((uint32_t)j);
+    }
+  jsb_graph* g = new (std::nothrow) jsb_graph();
+  if (!g) return fail(JSB_ENOMEM, "out of host memory");
+  int rc = finish_csr(g, n, &adj, nullptr, nullptr);
+  if (rc != JSB_OK) { delete g; return rc; }
+  *out = g;
+  return JSB_OK;
+}
+
+int64_t jsb_graph_nv(const jsb_graph* g) { return g ? g->nv : 0; }
+int64_t jsb_graph_ne(const jsb_graph* g) { return g ? g->ne : 0; }
+
+int jsb_graph_seed_candidates(jsb_graph* g, const int64_t** sites, int64_t* n) {
+  if (!g || !sites || !n) return fail(JSB_EINVAL, "null argument");
+  if (!g->have_cand) {
+    closeness_argmax(*g, g->cand);
+    g->have_cand = true;
+    g->d_cand_valid = false;
+  }
+  *sites = g->cand.data();
+  *n = (int64_t)g->cand.size();
+  return JSB_OK;
+}
+
+int jsb_graph_set_seed_candidates(jsb_graph* g, const int64_t* sites, int64_t n) {
+  if (!g || (n > 0 && !sites) || n < 0) return fail(JSB_EINVAL, "null argument");
+  for (int64_t i = 0; i < n; ++i)
+    if (sites[i] < 1 || sites[i] > g->nv) return fail(JSB_EINVAL, "seed candidate %lld is outside 1..nv", (long long)sites[i]);
+  g->cand.assign(sites, sites + n);
+  g->have_cand = true;
+  g->d_cand_valid = false;
+  return JSB_OK;
+}
+
+int jsb_graph_neighbors(const jsb_graph* g, int64_t site, int64_t* out, int cap) {
+  if (!g || site < 1 || site > g->nv) return fail(JSB_EINVAL, "site outside 1..nv");
+  std::vector<uint32_t> tmp((size_t)std::max(cap, 8));
+  int d = host_neighbors(*g, (uint32_t)(site - 1), tmp.data(), (int)tmp.size());
+  if (d > (int)tmp.size()) { tmp.resize(d); host_neighbors(*g, (uint32_t)(site - 1), tmp.data(), d); }
+  for (int i = 0; i < d && i < cap; ++i) out[i] = (int64_t)tmp[i] + 1;
+  return d;
+}
+
+void jsb_graph_free(jsb_graph* g) {
+  if (!g) return;
+  g->drop_device();
+  delete g;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Results
+// ------------------------------------------------------------------------------------------------
+struct jsb_result {
+  int64_t n_local = 0, n_points = 0, reps_per_point = 0, g_begin = 0;
+  uint32_t nv = 0;
+  uint32_t flags = 0;
+  int max_snap = 0;
+  std::vector<jsb_summary> summaries;
+  std::vector<long long> clone_off;
+  std::vector<jsb_clone> clones;
+  jsb_event* events = nullptr;  // pinned, replicate-major
+  std::vector<uint64_t> ev_off;  // n_local + 1
+  std::vector<uint16_t> lat_clone;
+  std::vector<uint32_t> lat_cell;
+  std::vector<uint32_t> lists;
+  std::vector<jsb_snapshot> snaps;
+  std::vector<int32_t> snap_count;
+  double kernel_ms = 0.0;
+  int64_t launches = 0;
+  ~jsb_result() {
+    if (events) cudaFreeHost(events);
+  }
+};
+
+namespace jsb {
+
+// Gathers the pool chunks of every replicate into one replicate-major array (coalesced 16-byte
+// copies), so that a single device-to-host copy moves exactly the rows that exist.
+__global__ void gather_log_kernel(const jsb_event* __restrict__ pool, const int32_t* __restrict__ owner,
+                                  const uint32_t* __restrict__ seq, const unsigned long long* __restrict__ ev_off,
+                                  uint32_t n_used, jsb_event* __restrict__ out) {
+  for (uint32_t c = blockIdx.x; c < n_used; c += gridDim.x) {
+    const int32_t o = owner[c];
+    const unsigned long long begin = ev_off[o], end = ev_off[o + 1];
+    const unsigned long long first = begin + (unsigned long long)seq[c] * kLogChunk;
+    if (first >= end) continue;
+    const unsigned long long cnt = (end - first) < (unsigned long long)kLogChunk ? (end - first) : (unsigned long long)kLogChunk;
+    const uint4* src = reinterpret_cast<const uint4*>(pool + (size_t)c * kLogChunk);
+    uint4* dst = reinterpret_cast<uint4*>(out + first);
+    for (unsigned long long i = threadIdx.x; i < cnt * 2; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
+}  // namespace jsb
+
+namespace {
+
+int validate_params(const jsb_graph* g, const jsb_params& p, int64_t idx) {
+  if (p.size != sizeof(jsb_params)) return fail(JSB_EINVAL, "points[%lld].size = %u, expected %zu (ABI mismatch)", (long long)idx, p.size, sizeof(jsb_params));
+  if (p.method != JSB_METHOD_RANDOM && p.method != JSB_METHOD_TREE) return fail(JSB_EINVAL, "points[%lld].method must be 1 or 2", (long long)idx);
+  if (p.rule < 0 || p.rule > 3) return fail(JSB_EINVAL, "points[%lld].rule must be 0..3", (long long)idx);
+  auto bad = [](double x) { return !(x >= 0.0) || std::isinf(x); };
+  if (std::isnan(p.Tf)) return fail(JSB_EINVAL, "points[%lld].Tf is NaN", (long long)idx);
+  if (bad(p.rate_death) || bad(p.rate_migration) || bad(p.mu_driver)) return fail(JSB_EINVAL, "points[%lld]: rates must be finite and >= 0", (long long)idx);
+  if (p.method == JSB_METHOD_RANDOM && (bad(p.rate_birth) || std::isnan(p.adv_mean) || bad(p.adv_std)))
+    return fail(JSB_EINVAL, "points[%lld]: rate_birth/adv_std must be finite and >= 0", (long long)idx);
+  if (p.n_start_cells < 0 || p.n_start_cells > g->nv) return fail(JSB_EINVAL, "points[%lld].n_start_cells must be in 0..nv", (long long)idx);
+  if (p.n_bottleneck < 0 || p.n_snapshots < 0) return fail(JSB_EINVAL, "points[%lld]: negative array length", (long long)idx);
+  if (p.n_bottleneck > 0 && (!p.t_bottleneck || !p.ratio_bottleneck)) return fail(JSB_EINVAL, "points[%lld]: t_bottleneck/ratio_bottleneck is null", (long long)idx);
+  for (int i = 0; i < p.n_bottleneck; ++i)
+    if (!(p.ratio_bottleneck[i] >= 0.0 && p.ratio_bottleneck[i] <= 1.0))
+      return fail(JSB_EINVAL, "points[%lld].ratio_bottleneck[%d] must be in [0,1] (the reference's sample() throws otherwise)", (long long)idx, i);
+  if (p.n_snapshots > 0 && !p.t_snapshot) return fail(JSB_EINVAL, "points[%lld].t_snapshot is null", (long long)idx);
+  if (p.method == JSB_METHOD_TREE) {
+    if (p.n_tree_nodes < 1 || p.n_tree_nodes > jsb::kMaxClones) return fail(JSB_EINVAL, "points[%lld].n_tree_nodes must be in 1..1000", (long long)idx);
+    if (p.n_tree_edges < 0 || (p.n_tree_edges > 0 && (!p.edge_parent || !p.edge_child))) return fail(JSB_EINVAL, "points[%lld]: edge list is null", (long long)idx);
+    if (!p.node_rate) return fail(JSB_EINVAL, "points[%lld].node_rate is null", (long long)idx);
+    if (p.root_node < 0 || p.root_node >= p.n_tree_nodes) return fail(JSB_EINVAL, "points[%lld].root_node out of range", (long long)idx);
+    for (int e = 0; e < p.n_tree_edges; ++e)
+      if (p.edge_parent[e] < 0 || p.edge_parent[e] >= p.n_tree_nodes || p.edge_child[e] < 0 || p.edge_child[e] >= p.n_tree_nodes)
+        return fail(JSB_EINVAL, "points[%lld]: edge %d names a node outside 0..n_tree_nodes-1", (long long)idx, e);
+    for (int i = 0; i < p.n_tree_nodes; ++i)
+      if (bad(p.node_rate[i])) return fail(JSB_EINVAL, "points[%lld].node_rate[%d] must be finite and >= 0", (long long)idx, i);
+    if (bad(p.root_rate)) return fail(JSB_EINVAL, "points[%lld].root_rate must be finite and >= 0", (long long)idx);
+  }
+  return JSB_OK;
+}
+
+int upload_graph(jsb_graph* g, int device) {
+  int rc = JSB_OK;
+  if (g->dev != device) {
+    g->drop_device();
+    g->dev = device;
+    if (g->kind == 1) {
+      CUDA_TRY(cudaMalloc(&g->d_rowptr, sizeof(uint32_t) * g->rowptr.size()));
+      CUDA_TRY(cudaMalloc(&g->d_colidx, sizeof(uint32_t) * std::max<size_t>(1, g->colidx.size())));
+      CUDA_TRY(cudaMemcpy(g->d_rowptr, g->rowptr.data(), sizeof(uint32_t) * g->rowptr.size(), cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpy(g->d_colidx, g->colidx.data(), sizeof(uint32_t) * g->colidx.size(), cudaMemcpyHostToDevice));
+    }
+  }
+  if (!g->d_cand_valid) {
+    cudaFree(g->d_cand);
+    g->d_cand = nullptr;
+    std::vector<uint32_t> c0(g->cand.size());
+    for (size_t i = 0; i < c0.size(); ++i) c0[i] = (uint32_t)(g->cand[i] - 1);
+    CUDA_TRY(cudaMalloc(&g->d_cand, sizeof(uint32_t) * std::max<size_t>(1, c0.size())));
+    CUDA_TRY(cudaMemcpy(g->d_cand, c0.data(), sizeof(uint32_t) * c0.size(), cudaMemcpyHostToDevice));
+    g->d_ncand = (uint32_t)c0.size();
+    g->d_cand_valid = true;
+  }
+done:
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t reps_per_point,
+            const jsb_run_opts* opts, jsb_result** out) {
+  using namespace jsb;
+  if (!out) return fail(JSB_EINVAL, "out is null");
+  *out = nullptr;
+  if (!g || !points || !opts) return fail(JSB_EINVAL, "null argument");
+  if (opts->size != sizeof(jsb_run_opts)) return fail(JSB_EINVAL, "opts.size = %u, expected %zu (ABI mismatch)", opts->size, sizeof(jsb_run_opts));
+  if (n_points < 1 || reps_per_point < 1) return fail(JSB_EINVAL, "n_points and reps_per_point must be >= 1");
+  if ((double)n_points * (double)reps_per_point > 4294967295.0) return fail(JSB_ECAPACITY, "more than 2^32-1 replicates");
+  const int64_t g_total = n_points * reps_per_point;
+  int64_t g_begin = opts->g_begin, g_end = opts->g_end == 0 ? g_total : opts->g_end;
+  if (g_begin < 0 || g_end > g_total || g_begin > g_end) return fail(JSB_EINVAL, "replicate range [%lld,%lld) is outside [0,%lld)", (long long)g_begin, (long long)g_end, (long long)g_total);
+  bool need_closeness = false;
+  for (int64_t i = 0; i < n_points; ++i) {
+    int rcv = validate_params(g, points[i], i);
+    if (rcv != JSB_OK) return rcv;
+    if (points[i].n_start_cells == 1) need_closeness = true;
+  }
+  int ndev = jsb_device_count();
+  if (ndev <= 0) return fail(JSB_ENODEVICE, "no CUDA device available; libjspace_b200 has no CPU fallback");
+  if (opts->device < 0 || opts->device >= ndev) return fail(JSB_EINVAL, "device %d is outside 0..%d", opts->device, ndev - 1);
+  if (need_closeness && !g->have_cand) {
+    const int64_t* s;
+    int64_t n;
+    jsb_graph_seed_candidates(g, &s, &n);
+  }
+
+  const int64_t n_local = g_end - g_begin;
+  int rc = JSB_OK;
+  jsb_result* res = new (std::nothrow) jsb_result();
+  if (!res) return fail(JSB_ENOMEM, "out of host memory");
+  res->n_local = n_local;
+  res->n_points = n_points;
+  res->reps_per_point = reps_per_point;
+  res->g_begin = g_begin;
+  res->nv = (uint32_t)g->nv;
+  res->flags = opts->flags;
+
+  // device buffers
+  DevPoint* d_points = nullptr;
+  double* d_dpool = nullptr;
+  int32_t* d_ipool = nullptr;
+  uint8_t* d_ws = nullptr;
+  jsb_summary* d_sum = nullptr;
+  jsb_clone* d_clones = nullptr;
+  unsigned long long* d_counters = nullptr;  // [0] work counter, [1] clone pool next
+  long long* d_clone_off = nullptr;
+  jsb_event *d_log = nullptr, *d_gather = nullptr;
+  uint32_t* d_chunk_next = nullptr;
+  int32_t* d_chunk_owner = nullptr;
+  uint32_t* d_chunk_seq = nullptr;
+  unsigned long long* d_ev_off = nullptr;
+  jsb_snapshot* d_snaps = nullptr;
+  uint16_t* d_out_clone = nullptr;
+  uint32_t *d_out_cell = nullptr, *d_out_lists = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream = nullptr;
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
+
+  if (n_local == 0) { *out = res; return JSB_OK; }
+
+  {
+    CUDA_TRY(cudaSetDevice(opts->device));
+    rc = upload_graph(g, opts->device);
+    if (rc != JSB_OK) goto done;
+    CUDA_TRY(cudaStreamCreate(&stream));
+
+    // ---- sweep points ---------------------------------------------------------------------
+    std::vector<DevPoint> hp((size_t)n_points);
+    std::vector<double> dpool(1, 0.0);
+    std::vector<int32_t> ipool(1, 0);
+    int max_snap = 0;
+    for (int64_t i = 0; i < n_points; ++i) {
+      const jsb_params& p = points[i];
+      DevPoint& d = hp[i];
+      std::memset(&d, 0, sizeof d);
+      d.Tf = p.Tf; d.rate_birth = p.rate_birth; d.rate_death = p.rate_death; d.rate_migration = p.rate_migration;
+      d.mu = p.mu_driver; d.adv_mean = p.adv_mean; d.adv_std = p.adv_std; d.root_rate = p.root_rate;
+      d.max_iter = p.max_iterations;
+      d.method = (int32_t)p.method; d.rule = p.rule; d.n_start = p.n_start_cells;
+      d.n_bott = p.n_bottleneck; d.n_snap = p.n_snapshots;
+      d.quirks = p.quirk_flags;
+      d.bott_off = (int32_t)dpool.size();
+      dpool.insert(dpool.end(), p.t_bottleneck, p.t_bottleneck + p.n_bottleneck);
+      dpool.insert(dpool.end(), p.ratio_bottleneck, p.ratio_bottleneck + p.n_bottleneck);
+      d.snap_off = (int32_t)dpool.size();
+      dpool.insert(dpool.end(), p.t_snapshot, p.t_snapshot + p.n_snapshots);
+      max_snap = std::max(max_snap, p.n_snapshots);
+      if (p.method == JSB_METHOD_TREE) {
+        d.n_nodes = p.n_tree_nodes; d.n_edges = p.n_tree_edges; d.root_node = p.root_node;
+        d.rate_off = (int32_t)dpool.size();
+        dpool.insert(dpool.end(), p.node_rate, p.node_rate + p.n_tree_nodes);
+        d.edge_off = (int32_t)ipool.size();
+        ipool.insert(ipool.end(), p.edge_parent, p.edge_parent + p.n_tree_edges);
+        ipool.insert(ipool.end(), p.edge_child, p.edge_child + p.n_tree_edges);
+      }
+    }
+    res->max_snap = max_snap;
+    CUDA_TRY(cudaMalloc(&d_points, sizeof(DevPoint) * hp.size()));
+    CUDA_TRY(cudaMalloc(&d_dpool, sizeof(double) * dpool.size()));
+    CUDA_TRY(cudaMalloc(&d_ipool, sizeof(int32_t) * ipool.size()));
+    CUDA_TRY(cudaMemcpyAsync(d_points, hp.data(), sizeof(DevPoint) * hp.size(), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d_dpool, dpool.data(), sizeof(double) * dpool.size(), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d_ipool, ipool.data(), sizeof(int32_t) * ipool.size(), cudaMemcpyHostToDevice, stream));
+
+    // ---- launch geometry ------------------------------------------------------------------
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, opts->device));
+    int blocks_per_sm = ssa_max_blocks_per_sm();
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    if (opts->warps_per_sm > 0) blocks_per_sm = std::max(1, std::min(blocks_per_sm, opts->warps_per_sm / kWarpsPerBlock));
+    int64_t want_blocks = (n_local + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    int grid = (int)std::min<int64_t>(want_blocks, (int64_t)prop.multiProcessorCount * blocks_per_sm);
+    const uint64_t slots = (uint64_t)grid * kWarpsPerBlock;
+
+    uint32_t arena_cap = (uint32_t)std::min<uint64_t>(4ull * g->nv + 2ull * kMinListCap * kTab, 0xFFFFFF00ull);
+    if (const char* dbg = std::getenv("JSB_DEBUG_ARENA_ENTRIES")) {  // test hook: force compactions
+      uint64_t v = std::strtoull(dbg, nullptr, 10);
+      arena_cap = (uint32_t)std::max<uint64_t>(v, 4096);  // too small -> JSB_ST_INTERNAL, never UB
+    }
+    const WsLayout L = ws_layout((uint32_t)g->nv, arena_cap);
+    CUDA_TRY(cudaMalloc(&d_ws, L.total * slots));
+
+    // ---- outputs --------------------------------------------------------------------------
+    CUDA_TRY(cudaMalloc(&d_sum, sizeof(jsb_summary) * n_local));
+    CUDA_TRY(cudaMalloc(&d_counters, sizeof(unsigned long long) * 2));
+    CUDA_TRY(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 2, stream));
+    unsigned long long clone_cap = std::min<unsigned long long>((unsigned long long)n_local * kMaxClones, 8ull << 20);
+    CUDA_TRY(cudaMalloc(&d_clones, sizeof(jsb_clone) * clone_cap));
+    CUDA_TRY(cudaMalloc(&d_clone_off, sizeof(long long) * n_local));
+    uint32_t n_chunks = 0;
+    if (opts->flags & JSB_OUT_EVENTS) {
+      size_t free_b = 0, total_b = 0;
+      CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+      uint64_t want = opts->log_pool_bytes ? opts->log_pool_bytes : (1ull << 30);
+      want = std::min<uint64_t>(want, free_b / 3);
+      n_chunks = (uint32_t)std::max<uint64_t>(1, want / (sizeof(jsb_event) * kLogChunk));
+      CUDA_TRY(cudaMalloc(&d_log, sizeof(jsb_event) * kLogChunk * (size_t)n_chunks));
+      CUDA_TRY(cudaMalloc(&d_chunk_next, sizeof(uint32_t)));
+      CUDA_TRY(cudaMemsetAsync(d_chunk_next, 0, sizeof(uint32_t), stream));
+      CUDA_TRY(cudaMalloc(&d_chunk_owner, sizeof(int32_t) * n_chunks));
+      CUDA_TRY(cudaMalloc(&d_chunk_seq, sizeof(uint32_t) * n_chunks));
+    }
+    if (max_snap > 0) {
+      CUDA_TRY(cudaMalloc(&d_snaps, sizeof(jsb_snapshot) * (size_t)max_snap * n_local));
+      CUDA_TRY(cudaMemsetAsync(d_snaps, 0xFF, sizeof(jsb_snapshot) * (size_t)max_snap * n_local, stream));
+    }
+    if (opts->flags & JSB_OUT_LATTICE) {
+      CUDA_TRY(cudaMalloc(&d_out_clone, sizeof(uint16_t) * (size_t)g->nv * n_local));
+      CUDA_TRY(cudaMalloc(&d_out_cell, sizeof(uint32_t) * (size_t)g->nv * n_local));
+    }
+    if (opts->flags & JSB_OUT_LISTS) CUDA_TRY(cudaMalloc(&d_out_lists, sizeof(uint32_t) * 2 * (size_t)g->nv * n_local));
+
+    RunArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.g.kind = g->kind; a.g.n1 = g->n1; a.g.n2 = g->n2; a.g.n3 = g->n3; a.g.nv = (uint32_t)g->nv;
+    a.g.rowptr = g->d_rowptr; a.g.colidx = g->d_colidx;
+    a.points = d_points; a.dpool = d_dpool; a.ipool = d_ipool;
+    a.seed_cand = g->d_cand; a.n_cand = g->d_ncand;
+    a.flags = opts->flags; a.seed = opts->seed; a.g_begin = g_begin; a.n_local = n_local; a.reps_per_point = reps_per_point;
+    a.ws = d_ws; a.ws_stride = L.total; a.arena_cap = arena_cap;
+    a.summaries = d_sum; a.clone_pool = d_clones; a.clone_pool_cap = clone_cap; a.clone_pool_next = d_counters + 1;
+    a.clone_off = d_clone_off;
+    a.log_pool = d_log; a.n_chunks = n_chunks; a.chunk_next = d_chunk_next; a.chunk_owner = d_chunk_owner; a.chunk_seq = d_chunk_seq;
+    a.snaps = d_snaps; a.max_snap = max_snap;
+    a.out_clone = d_out_clone; a.out_cell = d_out_cell; a.out_lists = d_out_lists;
+    a.work_counter = d_counters;
+
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    CUDA_TRY(cudaEventRecord(ev0, stream));
+    {
+      int lrc = launch_ssa(a, grid, stream);
+      if (lrc != 0) { rc = fail(JSB_ECUDA, "kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc)); goto done; }
+    }
+    res->launches = 1;
+    CUDA_TRY(cudaEventRecord(ev1, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
+      res->kernel_ms = ms;
+    }
+
+    // ---- copy back ------------------------------------------------------------------------
+    res->summaries.resize((size_t)n_local);
+    CUDA_TRY(cudaMemcpy(res->summaries.data(), d_sum, sizeof(jsb_summary) * n_local, cudaMemcpyDeviceToHost));
+    {
+      unsigned long long counters[2];
+      CUDA_TRY(cudaMemcpy(counters, d_counters, sizeof counters, cudaMemcpyDeviceToHost));
+      unsigned long long used = std::min(counters[1], clone_cap);
+      res->clones.resize((size_t)used);
+      res->clone_off.resize((size_t)n_local);
+      CUDA_TRY(cudaMemcpy(res->clones.data(), d_clones, sizeof(jsb_clone) * used, cudaMemcpyDeviceToHost));
+      CUDA_TRY(cudaMemcpy(res->clone_off.data(), d_clone_off, sizeof(long long) * n_local, cudaMemcpyDeviceToHost));
+    }
+    if (opts->flags & JSB_OUT_EVENTS) {
+      uint32_t used_chunks = 0;
+      CUDA_TRY(cudaMemcpy(&used_chunks, d_chunk_next, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      used_chunks = std::min(used_chunks, n_chunks);
+      std::vector<int32_t> owner(used_chunks);
+      CUDA_TRY(cudaMemcpy(owner.data(), d_chunk_owner, sizeof(int32_t) * used_chunks, cudaMemcpyDeviceToHost));
+      std::vector<uint32_t> chunks_of((size_t)n_local, 0);
+      for (uint32_t c = 0; c < used_chunks; ++c) chunks_of[owner[c]]++;
+      res->ev_off.assign((size_t)n_local + 1, 0);
+      for (int64_t i = 0; i < n_local; ++i) {
+        uint64_t logged = std::min<uint64_t>(res->summaries[i].n_events, (uint64_t)chunks_of[i] * kLogChunk);
+        res->ev_off[i + 1] = res->ev_off[i] + logged;
+      }
+      const uint64_t total = res->ev_off[n_local];
+      if (total > 0) {
+        CUDA_TRY(cudaMalloc(&d_gather, sizeof(jsb_event) * total));
+        CUDA_TRY(cudaMalloc(&d_ev_off, sizeof(unsigned long long) * (n_local + 1)));
+        CUDA_TRY(cudaMemcpyAsync(d_ev_off, res->ev_off.data(), sizeof(unsigned long long) * (n_local + 1), cudaMemcpyHostToDevice, stream));
+        int gblocks = (int)std::min<uint32_t>(used_chunks, (uint32_t)prop.multiProcessorCount * 8);
+        gather_log_kernel<<<gblocks, 256, 0, stream>>>(d_log, d_chunk_owner, d_chunk_seq, d_ev_off, used_chunks, d_gather);
+        CUDA_TRY(cudaGetLastError());
+        res->launches += 1;
+        CUDA_TRY(cudaHostAlloc((void**)&res->events, sizeof(jsb_event) * total, cudaHostAllocDefault));
+        CUDA_TRY(cudaMemcpyAsync(res->events, d_gather, sizeof(jsb_event) * total, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+      }
+    }
+    if (max_snap > 0) {
+      res->snaps.resize((size_t)max_snap * n_local);
+      CUDA_TRY(cudaMemcpy(res->snaps.data(), d_snaps, sizeof(jsb_snapshot) * res->snaps.size(), cudaMemcpyDeviceToHost));
+      res->snap_count.assign((size_t)n_local, 0);
+      for (int64_t i = 0; i < n_local; ++i) {
+        int c = 0;
+        while (c < max_snap && res->snaps[(size_t)i * max_snap + c].index != 0xFFFFFFFFu) ++c;
+        res->snap_count[i] = c;
+      }
+    }
+    if (opts->flags & JSB_OUT_LATTICE) {
+      res->lat_clone.resize((size_t)g->nv * n_local);
+      res->lat_cell.resize((size_t)g->nv * n_local);
+      CUDA_TRY(cudaMemcpy(res->lat_clone.data(), d_out_clone, sizeof(uint16_t) * res->lat_clone.size(), cudaMemcpyDeviceToHost));
+      CUDA_TRY(cudaMemcpy(res->lat_cell.data(), d_out_cell, sizeof(uint32_t) * res->lat_cell.size(), cudaMemcpyDeviceToHost));
+    }
+    if (opts->flags & JSB_OUT_LISTS) {
+      res->lists.resize(2 * (size_t)g->nv * n_local);
+      CUDA_TRY(cudaMemcpy(res->lists.data(), d_out_lists, sizeof(uint32_t) * res->lists.size(), cudaMemcpyDeviceToHost));
+    }
+  }
+
+done:
+  cudaFree(d_points); cudaFree(d_dpool); cudaFree(d_ipool); cudaFree(d_ws); cudaFree(d_sum); cudaFree(d_clones);
+  cudaFree(d_counters); cudaFree(d_clone_off); cudaFree(d_log); cudaFree(d_gather); cudaFree(d_chunk_next);
+  cudaFree(d_chunk_owner); cudaFree(d_chunk_seq); cudaFree(d_ev_off); cudaFree(d_snaps); cudaFree(d_out_clone);
+  cudaFree(d_out_cell); cudaFree(d_out_lists);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (stream) cudaStreamDestroy(stream);
+  cudaSetDevice(prev_dev);
+  if (rc != JSB_OK) { delete res; return rc; }
+  *out = res;
+  return JSB_OK;
+}
+
+int jsb_result_kernel_ms(const jsb_result* r, double* elapsed_ms) {
+  if (!r || !elapsed_ms) return fail(JSB_EINVAL, "null argument");
+  *elapsed_ms = r->kernel_ms;
+  return JSB_OK;
+}
+
+int jsb_result_launches(const jsb_result* r, int64_t* n) {
+  if (!r || !n) return fail(JSB_EINVAL, "null argument");
+  *n = r->launches;
+  return JSB_OK;
+}
+
+int64_t jsb_result_count(const jsb_result* r) { return r ? r->n_local : 0; }
+
+int jsb_result_summaries(const jsb_result* r, const jsb_summary** p) {
+  if (!r || !p) return fail(JSB_EINVAL, "null argument");
+  *p = r->summaries.data();
+  return JSB_OK;
+}
+
+#define CHECK_INDEX(r, i)                                                                          \
+  if (!(r)) return fail(JSB_EINVAL, "result is null");                                             \
+  if ((i) < 0 || (i) >= (r)->n_local) return fail(JSB_EINVAL, "replicate index %lld is outside 0..%lld", (long long)(i), (long long)(r)->n_local - 1)
+
+int jsb_result_clones(const jsb_result* r, int64_t i, const jsb_clone** p, int32_t* n) {
+  CHECK_INDEX(r, i);
+  if (!p || !n) return fail(JSB_EINVAL, "null argument");
+  long long off = r->clone_off[i];
+  if (off < 0) return fail(JSB_ECAPACITY, "clone pool overflowed; replicate %lld has no clone table", (long long)i);
+  *p = r->clones.data() + off;
+  *n = (int32_t)r->summaries[i].n_clones;
+  return JSB_OK;
+}
+
+int jsb_result_events(jsb_result* r, int64_t i, const jsb_event** p, int64_t* n) {
+  CHECK_INDEX(r, i);
+  if (!p || !n) return fail(JSB_EINVAL, "null argument");
+  if (!(r->flags & JSB_OUT_EVENTS)) return fail(JSB_EINVAL, "run did not request JSB_OUT_EVENTS");
+  *p = r->events ? r->events + r->ev_off[i] : nullptr;
+  *n = (int64_t)(r->ev_off[i + 1] - r->ev_off[i]);
+  return JSB_OK;
+}
+
+int jsb_result_lattice(const jsb_result* r, int64_t i, const uint16_t** clone, const uint32_t** cell_id) {
+  CHECK_INDEX(r, i);
+  if (!(r->flags & JSB_OUT_LATTICE)) return fail(JSB_EINVAL, "run did not request JSB_OUT_LATTICE");
+  if (clone) *clone = r->lat_clone.data() + (size_t)i * r->nv;
+  if (cell_id) *cell_id = r->lat_cell.data() + (size_t)i * r->nv;
+  return JSB_OK;
+}
+
+int jsb_result_list(jsb_result* r, int64_t i, int32_t list, const uint32_t** p, int64_t* n) {
+  CHECK_INDEX(r, i);
+  if (!p || !n) return fail(JSB_EINVAL, "null argument");
+  if (!(r->flags & JSB_OUT_LISTS)) return fail(JSB_EINVAL, "run did not request JSB_OUT_LISTS");
+  const jsb_summary& s = r->summaries[i];
+  if (list < 0 || list > (int32_t)s.n_clones) return fail(JSB_EINVAL, "list %d is outside 0..n_clones", list);
+  const uint32_t* base = r->lists.data() + (size_t)i * 2 * r->nv;
+  if (list == 0) { *p = base; *n = s.n_alive; return JSB_OK; }
+  const jsb_clone* c;
+  int32_t nc;
+  int rc = jsb_result_clones(r, i, &c, &nc);
+  if (rc != JSB_OK) return rc;
+  uint64_t off = 0;
+  for (int32_t k = 0; k < list - 1; ++k) off += c[k].count;
+  *p = base + r->nv + off;
+  *n = c[list - 1].count;
+  return JSB_OK;
+}
+
+int jsb_result_snapshots(const jsb_result* r, int64_t i, const jsb_snapshot** p, int32_t* n) {
+  CHECK_INDEX(r, i);
+  if (!p || !n) return fail(JSB_EINVAL, "null argument");
+  if (r->max_snap == 0) { *p = nullptr; *n = 0; return JSB_OK; }
+  *p = r->snaps.data() + (size_t)i * r->max_snap;
+  *n = r->snap_count[i];
+  return JSB_OK;
+}
+
+int jsb_result_histogram(const jsb_result* r, int64_t point, int kind, uint64_t out[64]) {
+  if (!r || !out) return fail(JSB_EINVAL, "null argument");
+  if (point < 0 || point >= r->n_points) return fail(JSB_EINVAL, "point %lld is outside 0..%lld", (long long)point, (long long)r->n_points - 1);
+  if (kind < 0 || kind > 2) return fail(JSB_EINVAL, "kind must be 0..2");
+  std::memset(out, 0, sizeof(uint64_t) * 64);
+  const int64_t lo = std::max<int64_t>(point * r->reps_per_point, r->g_begin);
+  const int64_t hi = std::min<int64_t>((point + 1) * r->reps_per_point, r->g_begin + r->n_local);
+  const uint64_t width = std::max<uint64_t>(1, ((uint64_t)r->nv + 63) / 64);
+  for (int64_t gi = lo; gi < hi; ++gi) {
+    const jsb_summary& s = r->summaries[gi - r->g_begin];
+    uint64_t bin;
+    if (kind == 0) bin = s.n_alive / width;
+    else if (kind == 1) bin = s.n_clones;
+    else { bin = 0; uint64_t v = s.n_iterations; while (v > 1) { v >>= 1; ++bin; } }
+    out[std::min<uint64_t>(bin, 63)]++;
+  }
+  return JSB_OK;
+}
+
+void jsb_result_free(jsb_result* r) { delete r; }
+
+// create_matrix_relational, src/sampling_phylogentic_relation_and_genotype.jl:60-104: walk the
+// Duplicate/Mutation rows backwards; a row whose Cell is currently in the sample list emits
+// (Father, Child, Time, Subpop_Child, Event) and replaces the child by its father.
+int jsb_result_genealogy(jsb_result* r, int64_t i, const uint32_t* sample_cells, int64_t n_samples,
+                         jsb_relation** rows, int64_t* n_rows) {
+  CHECK_INDEX(r, i);
+  if (!rows || !n_rows || (n_samples > 0 && !sample_cells)) return fail(JSB_EINVAL, "null argument");
+  if (!(r->flags & JSB_OUT_EVENTS)) return fail(JSB_EINVAL, "run did not request JSB_OUT_EVENTS");
+  const jsb_event* ev = r->events ? r->events + r->ev_off[i] : nullptr;
+  const int64_t n = (int64_t)(r->ev_off[i + 1] - r->ev_off[i]);
+  // every cell id appears as `cell` in at most one Duplicate/Mutation row (ids are unique), so
+  // the backward scan is a pointer chase: mark wanted ids, visit rows from the end.
+  std::vector<uint8_t> wanted((size_t)r->summaries[i].next_cell_id + 1, 0);
+  for (int64_t k = 0; k < n_samples; ++k) {
+    if (sample_cells[k] >= wanted.size()) return fail(JSB_EINVAL, "sample cell id %u was never created", sample_cells[k]);
+    wanted[sample_cells[k]] = 1;
+  }
+  std::vector<jsb_relation> outv;
+  for (int64_t k = n - 1; k >= 0; --k) {
+    const jsb_event& e = ev[k];
+    if (e.type != JSB_EV_DUPLICATE && e.type != JSB_EV_MUTATION) continue;  // :121-122
+    if (!wanted[e.cell]) continue;
+    wanted[e.cell] = 0;
+    wanted[e.parent] = 1;
+    jsb_relation rel;
+    std::memset(&rel, 0, sizeof rel);
+    rel.time = e.time;
+    rel.father = e.parent;
+    rel.child = e.cell;
+    // :86-96 — the reference looks the subpopulation up from mutations[end], which for a
+    // Mutation row is the FATHER's genotype (the new driver stripped), else the cell's own.
+    rel.subpop_child = e.clone;
+    if (e.type == JSB_EV_MUTATION && r->clone_off[i] >= 0) rel.subpop_child = r->clones[(size_t)r->clone_off[i] + e.clone - 1].parent;
+    rel.type = e.type;
+    outv.push_back(rel);
+  }
+  jsb_relation* buf = (jsb_relation*)std::malloc(sizeof(jsb_relation) * std::max<size_t>(1, outv.size()));
+  if (!buf) return fail(JSB_ENOMEM, "out of host memory");
+  std::memcpy(buf, outv.data(), sizeof(jsb_relation) * outv.size());
+  *rows = buf;
+  *n_rows = (int64_t)outv.size();
+  return JSB_OK;
+}
+
+void jsb_free(void* p) { std::free(p); }
+
+}  // extern "C"

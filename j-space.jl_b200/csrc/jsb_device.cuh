@@ -1,0 +1,115 @@
+// jsb_device.cuh — shared host/device declarations of the SSA engine (internal, not ABI).
+#pragma once
+#include <cstdint>
+
+#include "jspace_b200.h"
+
+namespace jsb {
+
+constexpr int kMaxClones = 1000;   // Set(1:1000), src/J_Space.jl:366
+constexpr int kTab = 1024;         // clone-table stride
+constexpr int kSmemClasses = 128;  // event classes (S+2) whose tables fit the per-warp smem slice
+constexpr int kLogChunk = 1024;    // records per event-log chunk (32 KB)
+constexpr int kMinListCap = 32;    // initial capacity of a ca_subpop list in the arena
+constexpr int kWarpsPerBlock = 4;
+
+// Draw sites of the draw contract; ctr.w = site << 28 | seq
+enum DrawSite : uint32_t {
+  DS_TIME_CLASS = 0,
+  DS_CELL_NBR = 1,
+  DS_DRIVER_COIN = 4,
+  DS_LABEL = 5,
+  DS_NORMAL = 6,
+  DS_EXCISION = 7,
+  DS_SEED_TIE = 9,
+  DS_SEED_POS = 10
+};
+
+struct DevGraph {
+  int kind;  // 0 = implicit lattice (n1 fastest), 1 = CSR
+  uint32_t n1, n2, n3;
+  uint32_t nv;
+  const uint32_t* rowptr;  // [nv+1]
+  const uint32_t* colidx;  // 0-based neighbour ids, ascending per row
+};
+
+struct DevPoint {
+  double Tf, rate_birth, rate_death, rate_migration, mu, adv_mean, adv_std, root_rate;
+  uint64_t max_iter;
+  int32_t method, rule, n_start, n_bott, n_snap, n_nodes, n_edges, root_node;
+  uint32_t quirks;
+  int32_t bott_off;  // into dpool: t_bottleneck[n_bott] then ratio[n_bott]
+  int32_t snap_off;  // into dpool: t_snapshot[n_snap]
+  int32_t rate_off;  // into dpool: node_rate[n_nodes]
+  int32_t edge_off;  // into ipool: edge_parent[n_edges] then edge_child[n_edges]
+  int32_t pad;
+};
+
+struct RunArgs {
+  DevGraph g;
+  const DevPoint* points;
+  const double* dpool;
+  const int32_t* ipool;
+  const uint32_t* seed_cand;  // 0-based candidate seed vertices (n_cell == 1)
+  uint32_t n_cand;
+  uint32_t flags;
+  uint64_t seed;
+  int64_t g_begin;
+  int64_t n_local;
+  int64_t reps_per_point;
+  // per-slot workspace
+  uint8_t* ws;
+  uint64_t ws_stride;
+  uint32_t arena_cap;  // entries
+  // outputs
+  jsb_summary* summaries;
+  jsb_clone* clone_pool;
+  unsigned long long clone_pool_cap;
+  unsigned long long* clone_pool_next;
+  long long* clone_off;  // per replicate, -1 = pool overflow
+  jsb_event* log_pool;
+  uint32_t n_chunks;
+  uint32_t* chunk_next;
+  int32_t* chunk_owner;
+  uint32_t* chunk_seq;
+  jsb_snapshot* snaps;
+  int32_t max_snap;
+  uint16_t* out_clone;
+  uint32_t* out_cell;
+  uint32_t* out_lists;  // [n_local][2][nv]: cs_alive then concatenated ca_subpop
+  unsigned long long* work_counter;
+};
+
+// Workspace layout per slot (all offsets 16-byte aligned); computed identically on host and device.
+struct WsLayout {
+  uint64_t clone, cellid, A, arena, inds, samp, c_off, c_len, c_cap, c_alpha, c_parent, c_label, g_w, g_c,
+      total;
+};
+__host__ __device__ inline uint64_t jsb_align16(uint64_t x) { return (x + 15) & ~uint64_t(15); }
+__host__ __device__ inline WsLayout ws_layout(uint32_t nv, uint32_t arena_cap) {
+  WsLayout L;
+  uint64_t o = 0;
+  L.clone = o;    o = jsb_align16(o + 2ull * nv);
+  L.cellid = o;   o = jsb_align16(o + 4ull * nv);
+  L.A = o;        o = jsb_align16(o + 4ull * (nv + 1));
+  L.arena = o;    o = jsb_align16(o + 4ull * arena_cap);
+  L.inds = o;     o = jsb_align16(o + 4ull * nv);
+  L.samp = o;     o = jsb_align16(o + 4ull * nv);
+  L.c_off = o;    o = jsb_align16(o + 4ull * kTab);
+  L.c_len = o;    o = jsb_align16(o + 4ull * kTab);
+  L.c_cap = o;    o = jsb_align16(o + 4ull * kTab);
+  L.c_alpha = o;  o = jsb_align16(o + 8ull * kTab);
+  L.c_parent = o; o = jsb_align16(o + 2ull * kTab);
+  L.c_label = o;  o = jsb_align16(o + 2ull * kTab);
+  L.g_w = o;      o = jsb_align16(o + 8ull * (kTab + 8));
+  L.g_c = o;      o = jsb_align16(o + 8ull * (kTab + 8));
+  L.total = (o + 255) & ~uint64_t(255);
+  return L;
+}
+
+// host-callable launch wrapper (jsb_kernels.cu)
+int launch_ssa(const RunArgs& args, int grid_blocks, void* stream);
+int ssa_max_blocks_per_sm();
+size_t ssa_smem_bytes();
+
+}  // namespace jsb

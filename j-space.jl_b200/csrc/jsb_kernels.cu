@@ -1,0 +1,1195 @@
+// jsb_kernels.cu — the ensemble SSA kernel (sm_100a).
+//
+// One independent replicate of the reference's `simulate_evolution` loop
+// (src/J_Space.jl:687-840 method 1, :904-1066 method 2) per WARP; persistent warps pull
+// replicate numbers from a global counter (replicate run lengths differ by orders of magnitude).
+//
+// How a warp runs a strictly sequential algorithm with 32 lanes:
+//   * The draw contract is counter-based (Philox4x32-10 keyed by seed, stream, iteration, draw
+//     site), so the random words of iterations it+1..it+32 are computed by 32 lanes at once.
+//   * 79-97 % of the reference's iterations are null events (target site occupied) that do not
+//     change any state.  The warp therefore evaluates 32 consecutive iterations speculatively
+//     against the current state (class selection, member lookup, neighbour, occupancy test), finds
+//     the first lane whose iteration changes state (ballot + ffs), commits all earlier
+//     null iterations in one go, applies that one event cooperatively (parallel list shifts,
+//     searches, log stores) and re-speculates from the next iteration.
+//   * Event times are the only sequential fp64 chain (t += θ·e); it is run over the committed
+//     lanes only, and the per-lane times are materialised only when the batch may touch Tf, an
+//     excision time or a snapshot time.
+// Everything that must match the reference bit-for-bit (sum order of Σα·n, the pairwise cumsum,
+// insertion-ordered lists with stable deletes) is kept in the reference's order; see DESIGN.md.
+//
+// fp64 determinism: this translation unit is compiled with -fmad=false and uses only IEEE
+// + - * / sqrt in a fixed association, so event times and fitness values are bit-identical to
+// the CPU oracle's.
+
+#include <cuda_runtime.h>
+
+#include "jsb_device.cuh"
+
+namespace jsb {
+
+#define FULL 0xffffffffu
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 and the draw contract
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t o[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    if (r > 0) {
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+struct Key {
+  uint32_t k0, k1, stream;
+};
+
+__device__ __forceinline__ void draw_block(const Key& key, uint64_t iter, uint32_t attempt, uint32_t site,
+                                           uint32_t seq, uint64_t& a, uint64_t& b) {
+  uint32_t o[4];
+  philox4x32_10((uint32_t)iter, ((uint32_t)(iter >> 32) & 0xFFFFu) | (attempt << 16), key.stream,
+                (site << 28) | (seq & 0x0FFFFFFFu), key.k0, key.k1, o);
+  a = (uint64_t)o[0] | ((uint64_t)o[1] << 32);
+  b = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
+}
+
+// Lemire's nearly-divisionless bounded draw; `w` is attempt 0 of (iter, site, seq, half).
+__device__ __forceinline__ uint32_t bounded(const Key& key, uint64_t w, uint32_t s, uint64_t iter, uint32_t site,
+                                            uint32_t seq, int half) {
+  uint64_t hi = __umul64hi(w, (uint64_t)s);
+  uint64_t lo = w * (uint64_t)s;
+  if (lo < (uint64_t)s) {  // probability s / 2^64
+    uint64_t t = (0ull - (uint64_t)s) % (uint64_t)s;
+    uint32_t attempt = 0;
+    while (lo < t) {
+      ++attempt;
+      uint64_t a, b;
+      draw_block(key, iter, attempt, site, seq, a, b);
+      w = half ? b : a;
+      hi = __umul64hi(w, (uint64_t)s);
+      lo = w * (uint64_t)s;
+    }
+  }
+  return (uint32_t)hi;
+}
+
+__device__ __forceinline__ double u01_53(uint64_t w) { return (double)(w >> 11) * 0x1.0p-53; }
+__device__ __forceinline__ double u01_open(uint64_t w) { return ((double)(w >> 12) + 0.5) * 0x1.0p-52; }
+
+// Natural log for positive normal doubles, the single-path fdlibm/musl form; the association
+// below is part of the draw contract.
+__device__ __forceinline__ double contract_log(double x) {
+  const double ln2_hi = 0x1.62e42fee00000p-1, ln2_lo = 0x1.a39ef35793c76p-33, Lg1 = 0x1.5555555555593p-1,
+               Lg2 = 0x1.999999997fa04p-2, Lg3 = 0x1.2492494229359p-2, Lg4 = 0x1.c71c51d8e78afp-3,
+               Lg5 = 0x1.7466496cb03dep-3, Lg6 = 0x1.39a09d078c69fp-3, Lg7 = 0x1.2f112df3e5244p-3;
+  uint32_t hx = (uint32_t)__double2hiint(x);
+  uint32_t lx = (uint32_t)__double2loint(x);
+  hx += 0x3ff00000u - 0x3fe6a09eu;
+  int k = (int)(hx >> 20) - 0x3ff;
+  hx = (hx & 0x000fffffu) + 0x3fe6a09eu;
+  x = __hiloint2double((int)hx, (int)lx);
+  double f = x - 1.0;
+  double hfsq = (0.5 * f) * f;
+  double s = f / (2.0 + f);
+  double z = s * s;
+  double w = z * z;
+  double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+  double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+  double R = t2 + t1;
+  double dk = (double)k;
+  return (((s * (hfsq + R) + dk * ln2_lo) - hfsq) + f) + dk * ln2_hi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Graph access (0-based vertices on the device; the ABI adds 1)
+// ---------------------------------------------------------------------------------------------
+// Implicit lattice of Graphs.grid((n1,n2,n3)): vertex = x + y*n1 + z*n1*n2, neighbours ascending:
+// z-1, y-1, x-1, x+1, y+1, z+1.
+__device__ __forceinline__ uint32_t lattice_mask(const DevGraph& g, uint32_t v) {
+  uint32_t x = v % g.n1;
+  uint32_t yz = v / g.n1;
+  uint32_t y = yz % g.n2;
+  uint32_t z = yz / g.n2;
+  return (uint32_t)(z > 0) | ((uint32_t)(y > 0) << 1) | ((uint32_t)(x > 0) << 2) | ((uint32_t)(x + 1 < g.n1) << 3) |
+         ((uint32_t)(y + 1 < g.n2) << 4) | ((uint32_t)(z + 1 < g.n3) << 5);
+}
+__device__ __forceinline__ uint32_t lattice_pick(const DevGraph& g, uint32_t v, uint32_t mask, uint32_t j) {
+  int bit = 0;
+#pragma unroll
+  for (int b = 0; b < 6; ++b) {
+    bool here = ((mask >> b) & 1u) && (__popc(mask & ((1u << b) - 1u)) == (int)j);
+    if (here) bit = b;
+  }
+  uint32_t plane = g.n1 * g.n2;
+  switch (bit) {
+    case 0: return v - plane;
+    case 1: return v - g.n1;
+    case 2: return v - 1;
+    case 3: return v + 1;
+    case 4: return v + g.n1;
+    default: return v + plane;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-replicate context
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+  const RunArgs* A;
+  const DevPoint* P;
+  const double *tb, *ratio, *tsnap, *node_rate;
+  const int32_t *edge_parent, *edge_child;
+  uint16_t* clone;
+  uint32_t *cellid, *Alist, *arena, *inds, *samp;
+  uint32_t *c_off, *c_len, *c_cap;
+  double* c_alpha;
+  uint16_t *c_parent, *c_label;
+  double *g_w, *g_c, *s_w, *s_c;
+  double *w, *c;  // active class tables: shared slice while S+2 <= kSmemClasses, else global
+  Key key;
+  int64_t local_idx;
+  int lane;
+};
+
+struct Rep {
+  double t, theta;
+  uint64_t it, nlog;
+  uint32_t n, S, next_id, arena_top, cur_chunk, used_w;
+  int bott_id, snap_idx, status;
+  uint32_t n_eff, n_births, n_deaths, n_migr, n_disp, n_exc;
+  bool log_on;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Event log: 32-byte records in pool chunks, rows in the reference's push! order
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool log_open_chunk(Ctx& X, Rep& r) {
+  uint32_t c = 0;
+  if (X.lane == 0) {
+    c = atomicAdd(X.A->chunk_next, 1u);
+    if (c < X.A->n_chunks) {
+      X.A->chunk_owner[c] = (int32_t)X.local_idx;
+      X.A->chunk_seq[c] = (uint32_t)(r.nlog / kLogChunk);
+    }
+  }
+  c = __shfl_sync(FULL, c, 0);
+  if (c >= X.A->n_chunks) {
+    r.log_on = false;
+    r.status = JSB_ST_LOG_OVERFLOW;
+    return false;
+  }
+  r.cur_chunk = c;
+  return true;
+}
+
+__device__ __forceinline__ void log_store(jsb_event* dst, int lane_sel, double time, uint32_t cell, uint32_t parent,
+                                          uint32_t site, uint32_t site2, uint32_t clone, uint32_t label, uint32_t type,
+                                          uint32_t flags) {
+  // two 16-byte stores = one full 32-byte sector
+  uint4 v;
+  if (lane_sel == 0) {
+    v.x = (uint32_t)__double2loint(time);
+    v.y = (uint32_t)__double2hiint(time);
+    v.z = cell;
+    v.w = parent;
+  } else {
+    v.x = site;
+    v.y = site2;
+    v.z = (clone & 0xFFFFu) | (label << 16);
+    v.w = (type & 0xFFu) | ((flags & 0xFFu) << 8);
+  }
+  reinterpret_cast<uint4*>(dst)[lane_sel] = v;
+}
+
+__device__ __forceinline__ void log_row(Ctx& X, Rep& r, uint32_t type, uint32_t flags, double time, uint32_t cell,
+                                        uint32_t parent, uint32_t site0, uint32_t site2_0, uint32_t clone,
+                                        uint32_t label) {
+  if (r.log_on) {
+    uint32_t slot = (uint32_t)(r.nlog % kLogChunk);
+    if (slot == 0) log_open_chunk(X, r);
+    if (r.log_on && X.lane < 2) {
+      jsb_event* dst = X.A->log_pool + (size_t)r.cur_chunk * kLogChunk + slot;
+      log_store(dst, X.lane, time, cell, parent, site0 + 1, site2_0, clone, label, type, flags);
+    }
+  }
+  r.nlog++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ordered lists.  cs_alive is one array; the ca_subpop lists live in an arena as contiguous
+// blocks (offset, len, cap) so that `list[x]` is a single load.  filter!(e -> e != v, list) is a
+// parallel search + left shift (stable).  Blocks grow by doubling; when the arena is exhausted
+// it is compacted in place (dead space squeezed out, order inside every list untouched).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t list_find(const uint32_t* list, uint32_t len, uint32_t value, int lane) {
+  for (uint32_t base = 0; base < len; base += 32) {
+    uint32_t i = base + lane;
+    bool hit = (i < len) && (list[i] == value);
+    uint32_t m = __ballot_sync(FULL, hit);
+    if (m) return base + (uint32_t)__ffs(m) - 1u;
+  }
+  return 0xFFFFFFFFu;
+}
+
+// remove list[idx], keep order
+__device__ __forceinline__ void list_remove_at(uint32_t* list, uint32_t len, uint32_t idx, int lane) {
+  for (uint32_t base = idx; base + 1 < len; base += 32) {
+    uint32_t i = base + lane;
+    uint32_t v = 0;
+    if (i + 1 < len) v = list[i + 1];
+    __syncwarp();
+    if (i + 1 < len) list[i] = v;
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ uint32_t gc_cap(uint32_t len) {
+  return len * 2 > (uint32_t)kMinListCap ? len * 2 : (uint32_t)kMinListCap;
+}
+
+// Arena compaction, in place, order inside every list untouched.  Pass 1 squeezes the blocks
+// down in ascending-offset order (cap = len); pass 2 spreads them out again from the last block
+// to the first so that block i gets cap = max(min, 2*len).  Visited blocks are tagged in the top
+// bit of cap.  O(S^2/32) bookkeeping — only runs when clone turnover has fragmented the arena.
+__device__ void arena_gc(Ctx& X, Rep& r) {
+  const int lane = X.lane;
+  uint32_t top = 0;
+  for (uint32_t step = 0; step < r.S; ++step) {
+    uint32_t best = 0xFFFFFFFFu, besti = 0xFFFFFFFFu;
+    for (uint32_t i = lane; i < r.S; i += 32) {
+      uint32_t o = X.c_off[i];
+      if (!(X.c_cap[i] & 0x80000000u) && o < best) { best = o; besti = i; }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+      uint32_t ob = __shfl_xor_sync(FULL, best, d), oi = __shfl_xor_sync(FULL, besti, d);
+      if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    const uint32_t i = besti, l = X.c_len[i], src = best;
+    if (top != src) {
+      for (uint32_t b = 0; b < l; b += 32) {  // dst < src: ascending chunks are safe
+        uint32_t k = b + lane;
+        uint32_t v = 0;
+        if (k < l) v = X.arena[src + k];
+        __syncwarp();
+        if (k < l) X.arena[top + k] = v;
+        __syncwarp();
+      }
+    }
+    if (lane == 0) {
+      X.c_off[i] = top;
+      X.c_cap[i] = l | 0x80000000u;
+    }
+    __syncwarp();
+    top += l;
+  }
+  uint32_t total = 0;
+  for (uint32_t i = lane; i < r.S; i += 32) total += gc_cap(X.c_len[i]);
+  for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
+  if (total > X.A->arena_cap) {  // cannot happen when arena_cap >= 2*nv + kMinListCap*kTab
+    for (uint32_t i = lane; i < r.S; i += 32) X.c_cap[i] &= 0x7FFFFFFFu;
+    __syncwarp();
+    r.arena_top = top;
+    r.status = JSB_ST_INTERNAL;
+    return;
+  }
+  for (uint32_t step = 0; step < r.S; ++step) {
+    // still-tagged block with the largest (squeezed offset, index)
+    uint32_t best = 0, besti = 0xFFFFFFFFu;
+    for (uint32_t i = lane; i < r.S; i += 32) {
+      uint32_t o = X.c_off[i];
+      if ((X.c_cap[i] & 0x80000000u) && (besti == 0xFFFFFFFFu || o > best || (o == best && i > besti))) {
+        best = o; besti = i;
+      }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+      uint32_t ob = __shfl_xor_sync(FULL, best, d), oi = __shfl_xor_sync(FULL, besti, d);
+      if (oi != 0xFFFFFFFFu && (besti == 0xFFFFFFFFu || ob > best || (ob == best && oi > besti))) {
+        best = ob; besti = oi;
+      }
+    }
+    const uint32_t i = besti, l = X.c_len[i], src = best;
+    // new offset = total new capacity of the blocks not visited yet (all lie below src)
+    uint32_t noff = 0;
+    for (uint32_t q = lane; q < r.S; q += 32)
+      if (q != i && (X.c_cap[q] & 0x80000000u)) noff += gc_cap(X.c_len[q]);
+    for (int d = 16; d > 0; d >>= 1) noff += __shfl_xor_sync(FULL, noff, d);
+    if (noff != src && l > 0) {
+      for (uint32_t cb = (l + 31) / 32; cb-- > 0;) {  // dst > src: descending chunks are safe
+        uint32_t k = cb * 32 + lane;
+        uint32_t v = 0;
+        if (k < l) v = X.arena[src + k];
+        __syncwarp();
+        if (k < l) X.arena[noff + k] = v;
+        __syncwarp();
+      }
+    }
+    if (lane == 0) {
+      X.c_off[i] = noff;
+      X.c_cap[i] = gc_cap(l);
+    }
+    __syncwarp();
+  }
+  r.arena_top = total;
+}
+
+// make room for one more element in list c (0-based clone index); returns false on failure
+__device__ bool list_reserve(Ctx& X, Rep& r, uint32_t c) {
+  uint32_t len = X.c_len[c], cap = X.c_cap[c];
+  if (len < cap) return true;
+  uint32_t ncap = cap * 2;
+  if (r.arena_top + ncap > X.A->arena_cap) {
+    arena_gc(X, r);
+    if (r.status == JSB_ST_INTERNAL) return false;
+    len = X.c_len[c];
+    cap = X.c_cap[c];
+    if (len < cap) return true;
+    ncap = cap * 2;
+    if (r.arena_top + ncap > X.A->arena_cap) { r.status = JSB_ST_INTERNAL; return false; }
+  }
+  // relocate to the top of the arena with doubled capacity
+  const uint32_t src = X.c_off[c], dst = r.arena_top;
+  for (uint32_t b = 0; b < len; b += 32) {
+    uint32_t k = b + X.lane;
+    if (k < len) X.arena[dst + k] = X.arena[src + k];
+  }
+  __syncwarp();
+  if (X.lane == 0) {
+    X.c_off[c] = dst;
+    X.c_cap[c] = ncap;
+  }
+  __syncwarp();
+  r.arena_top += ncap;
+  return true;
+}
+
+__device__ __forceinline__ bool list_append(Ctx& X, Rep& r, uint32_t c, uint32_t site) {
+  if (!list_reserve(X, r, c)) return false;
+  if (X.lane == 0) {
+    uint32_t len = X.c_len[c];
+    X.arena[X.c_off[c] + len] = site;
+    X.c_len[c] = len + 1;
+  }
+  __syncwarp();
+  return true;
+}
+
+// filter!(e -> e != site, ca_subpop[c])
+__device__ __forceinline__ void list_remove_value(Ctx& X, uint32_t c, uint32_t site) {
+  uint32_t len = X.c_len[c];
+  uint32_t* list = X.arena + X.c_off[c];
+  uint32_t idx = list_find(list, len, site, X.lane);
+  if (idx != 0xFFFFFFFFu) {
+    list_remove_at(list, len, idx, X.lane);
+    if (X.lane == 0) X.c_len[c] = len - 1;
+    __syncwarp();
+  }
+}
+
+__device__ bool new_clone(Ctx& X, Rep& r, uint32_t parent1, uint32_t label, double alpha, uint32_t first_site) {
+  const uint32_t c = r.S;
+  if (r.arena_top + kMinListCap > X.A->arena_cap) {
+    arena_gc(X, r);
+    if (r.status == JSB_ST_INTERNAL) return false;
+    if (r.arena_top + kMinListCap > X.A->arena_cap) { r.status = JSB_ST_INTERNAL; return false; }
+  }
+  if (X.lane == 0) {
+    X.c_off[c] = r.arena_top;
+    X.c_len[c] = 1;
+    X.c_cap[c] = kMinListCap;
+    X.c_alpha[c] = alpha;
+    X.c_parent[c] = (uint16_t)parent1;
+    X.c_label[c] = (uint16_t)label;
+    X.arena[r.arena_top] = first_site;
+  }
+  __syncwarp();
+  r.arena_top += kMinListCap;
+  r.S = c + 1;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Class table: λ, θ and prob_cum of src/J_Space.jl:690-718, in the reference's summation order
+// ---------------------------------------------------------------------------------------------
+__device__ double acc_pairwise(double* __restrict__ v, double* __restrict__ c, double s, int i1, int n,
+                               double& mx, int lane) {
+  // Base._accumulate_pairwise! (Julia 1.7.3): blocks of < 128 are sequential; c holds the
+  // running maximum of prob_cum so that lower_bound == findfirst(k .<= prob_cum)
+  if (n < 128) {
+    double s_ = v[i1];
+    double cv = s + s_;
+    mx = cv > mx ? cv : mx;
+    if (lane == 0) c[i1] = mx;
+    for (int i = i1 + 1; i < i1 + n; ++i) {
+      s_ = s_ + v[i];
+      cv = s + s_;
+      mx = cv > mx ? cv : mx;
+      if (lane == 0) c[i] = mx;
+    }
+    return s_;
+  }
+  int n2 = n >> 1;
+  double sl = acc_pairwise(v, c, s, i1, n2, mx, lane);
+  double sr = acc_pairwise(v, c, s + sl, i1 + n2, n - n2, mx, lane);
+  return sl + sr;
+}
+
+__device__ void rebuild_classes(Ctx& X, Rep& r) {
+  const int S = (int)r.S;
+  const int ncls = S + 2;
+  if (ncls <= kSmemClasses) { X.w = X.s_w; X.c = X.s_c; } else { X.w = X.g_w; X.c = X.g_c; }
+  double* __restrict__ w = X.w;
+  double* __restrict__ c = X.c;
+  for (int i = X.lane; i < S; i += 32) w[i] = X.c_alpha[i] * (double)X.c_len[i];  // :692-694
+  __syncwarp();
+  double birth = w[0];  // sum(α_subpop): sequential left fold
+  for (int i = 1; i < S; ++i) birth = birth + w[i];
+  double death = X.P->rate_death * (double)r.n;        // :696
+  double M = X.P->rate_migration * (double)r.n;        // :697
+  double lambda = birth + death + M;                   // :698
+  r.theta = 1.0 / lambda;                              // Exponential(1 / λ) :699
+  __syncwarp();
+  for (int i = X.lane; i < S; i += 32) w[i] = w[i] / lambda;  // Aₙ :703
+  if (X.lane == 0) {
+    w[S] = death / lambda;   // Bₙ :704
+    w[S + 1] = M / lambda;   // Mₙ :705
+  }
+  __syncwarp();
+  // prob_cum = cumsum(prob_vet) :718
+  double v1 = w[0];
+  if (X.lane == 0) c[0] = v1;
+  double mx = v1;
+  acc_pairwise(w, c, v1, 1, ncls - 1, mx, X.lane);
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// One speculative evaluation of iteration q against the current state (per lane)
+// ---------------------------------------------------------------------------------------------
+struct Eval {
+  uint32_t cls;   // 0..S-1 birth of clone cls+1, S death, S+1 migration, S+2 none
+  uint32_t x;     // index into the member list
+  uint32_t cell;  // 0-based vertex
+  uint32_t pos;   // 0-based vertex
+  uint32_t occ;   // clone id at pos (0 = empty)
+  bool effective;
+};
+
+__device__ __forceinline__ Eval evaluate(const Ctx& X, const Rep& r, uint64_t q, uint64_t w_class, uint64_t w_cell,
+                                         uint64_t w_nbr) {
+  Eval e;
+  e.x = 0; e.cell = 0; e.pos = 0; e.occ = 0; e.effective = false;
+  const uint32_t S = r.S;
+  const double k = u01_53(w_class);  // :721
+  // findfirst(k .<= prob_cum) :722-723 as a lower bound on the running maximum
+  const double* c = X.c;
+  uint32_t lo = 0, len = S + 2;
+  while (len > 0) {
+    uint32_t half = len >> 1;
+    if (c[lo + half] < k) { lo += half + 1; len -= half + 1; } else { len = half; }
+  }
+  e.cls = lo;
+  if (lo >= S + 2) return e;  // reference: findfirst -> nothing; contract: null iteration
+  const uint32_t* list;
+  uint32_t llen;
+  if (lo < S) { list = X.arena + X.c_off[lo]; llen = X.c_len[lo]; } else { list = X.Alist; llen = r.n; }
+  if (llen == 0) return e;    // rand(1:0) throws in the reference; contract: null iteration
+  e.x = bounded(X.key, w_cell, llen, q, DS_CELL_NBR, 0, 0);  // :727 / :746 / :762
+  e.cell = list[e.x];
+  if (lo == S) { e.effective = true; return e; }  // death :744-759 needs no neighbour
+  const DevGraph& g = X.A->g;
+  uint32_t deg, mask = 0, row0 = 0;
+  if (g.kind == 0) { mask = lattice_mask(g, e.cell); deg = (uint32_t)__popc(mask); }
+  else { row0 = g.rowptr[e.cell]; deg = g.rowptr[e.cell + 1] - row0; }
+  if (deg == 0) return e;     // rand on an empty neighbour list throws; contract: null iteration
+  uint32_t j = bounded(X.key, w_nbr, deg, q, DS_CELL_NBR, 0, 1);  // :730 / :764
+  e.pos = (g.kind == 0) ? lattice_pick(g, e.cell, mask, j) : g.colidx[row0 + j];
+  e.occ = X.clone[e.pos];
+  if (lo == S + 1) { e.effective = (e.occ == 0); return e; }  // migration :732
+  bool rule = true;  // :767-786
+  const int model = X.P->rule;
+  if (model == JSB_RULE_CONTACT) rule = (e.occ == 0);
+  else if (model == JSB_RULE_VOTER) rule = !(e.occ != 0 && e.occ == lo + 1);
+  else if (model == JSB_RULE_HVOTER) rule = !(e.occ != 0 && X.c_alpha[lo] <= X.c_alpha[e.occ - 1]);
+  e.effective = rule;
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Event application (whole warp cooperates; control flow is warp-uniform)
+// ---------------------------------------------------------------------------------------------
+__device__ void apply_migration(Ctx& X, Rep& r, const Eval& e) {  // :733-741, migration_cell :592-613
+  uint32_t cid = X.cellid[e.cell];
+  uint32_t cl = X.clone[e.cell];
+  __syncwarp();
+  if (X.lane == 0) {
+    X.clone[e.cell] = 0;
+    X.clone[e.pos] = (uint16_t)cl;
+    X.cellid[e.pos] = cid;
+    X.Alist[r.n] = e.pos;  // push!(cs_alive, pos)
+  }
+  __syncwarp();
+  log_row(X, r, JSB_EV_MIGRATION, JSB_EVF_GROUP_START, r.t, cid, 0, e.pos, e.cell + 1, cl, 0);
+  list_append(X, r, cl - 1, e.pos);                 // push!(ca_subpop[idx], pos)
+  list_remove_at(X.Alist, r.n + 1, e.x, X.lane);    // filter!(e -> e != cell, cs_alive)
+  list_remove_value(X, cl - 1, e.cell);             // filter!(e -> e != cell, ca_subpop[idx])
+  r.n_eff++;
+  r.n_migr++;
+}
+
+__device__ void apply_death(Ctx& X, Rep& r, const Eval& e) {  // :746-759, cell_death :574-586
+  uint32_t cid = X.cellid[e.cell];
+  uint32_t cl = X.clone[e.cell];
+  __syncwarp();
+  log_row(X, r, JSB_EV_DEATH, JSB_EVF_GROUP_START, r.t, cid, 0, e.cell, 0, cl, 0);
+  if (X.lane == 0) X.clone[e.cell] = 0;
+  __syncwarp();
+  list_remove_at(X.Alist, r.n, e.x, X.lane);
+  list_remove_value(X, cl - 1, e.cell);
+  r.n -= 1;
+  r.n_eff++;
+  r.n_deaths++;
+}
+
+// j-th (0-based) unused label of 1..1000; lane l owns labels 32l..32l+31
+__device__ __forceinline__ uint32_t pick_label(Rep& r, uint32_t j, int lane) {
+  uint32_t freew = ~r.used_w;
+  uint32_t cnt = (uint32_t)__popc(freew);
+  uint32_t incl = cnt;
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += o;
+  }
+  uint32_t excl = incl - cnt;
+  bool mine = (j >= excl) && (j < incl);
+  uint32_t lab = 0;
+  if (mine) {
+    uint32_t k = j - excl;  // k-th set bit of freew
+    uint32_t m = freew;
+    for (uint32_t q = 0; q < k; ++q) m &= m - 1;
+    uint32_t bit = (uint32_t)__ffs(m) - 1u;
+    lab = (uint32_t)lane * 32u + bit;
+    r.used_w |= 1u << bit;
+  }
+  uint32_t who = __ballot_sync(FULL, mine);
+  return __shfl_sync(FULL, lab, __ffs(who) - 1);
+}
+
+// randn by the polar method on contract draws (D9)
+__device__ double contract_randn(const Ctx& X, uint64_t iter) {
+  for (uint32_t attempt = 0;; ++attempt) {
+    uint64_t a, b;
+    draw_block(X.key, iter, 0, DS_NORMAL, attempt, a, b);
+    double v1 = 2.0 * u01_53(a) - 1.0;
+    double v2 = 2.0 * u01_53(b) - 1.0;
+    double s = v1 * v1 + v2 * v2;
+    if (s >= 1.0 || s == 0.0) continue;
+    return v1 * sqrt((-2.0 * contract_log(s)) / s);
+  }
+}
+
+// cell_birth :320-416 / :419-537 plus the caller's bookkeeping :803-808.  Returns false when the
+// replicate must stop.
+__device__ bool apply_birth(Ctx& X, Rep& r, const Eval& e) {
+  const DevPoint& P = *X.P;
+  const uint32_t sp = e.cls + 1;  // :Subpop of the dividing cell (== min)
+  uint64_t wa, wb;
+  draw_block(X.key, r.it, 0, DS_DRIVER_COIN, 0, wa, wb);
+  const double rr = u01_53(wa);  // :347 / :447
+  int child_node = -1;
+  bool driver;
+  if (P.method == JSB_METHOD_TREE) {
+    if (rr <= P.mu) {  // :448
+      int last = (int)X.c_label[sp - 1] - 1;
+      for (int ed = 0; ed < P.n_edges && child_node < 0; ++ed) {  // edge-list order :456
+        if (X.edge_parent[ed] != last) continue;
+        int cand = X.edge_child[ed];
+        bool present = false;  // new_mut ∈ set_mut :466
+        for (uint32_t s0 = X.lane; s0 < r.S; s0 += 32)
+          if (X.c_parent[s0] == sp && (int)X.c_label[s0] - 1 == cand) present = true;
+        present = __any_sync(FULL, present);
+        if (!present) child_node = cand;
+      }
+    }
+    driver = child_node >= 0;  // :476
+  } else {
+    driver = !(rr > P.mu);  // :348
+  }
+  if (driver && r.S >= (uint32_t)kMaxClones) {  // reference throws at :371
+    r.status = JSB_ST_CLONE_CAPACITY;
+    return false;
+  }
+  uint32_t first_flag = JSB_EVF_GROUP_START;
+  if (e.occ != 0) {  // :335-338 displacement (voter rules)
+    uint32_t pid = X.cellid[e.pos];
+    __syncwarp();
+    list_remove_value(X, e.occ - 1, e.pos);
+    log_row(X, r, JSB_EV_DEATH, JSB_EVF_DISPLACED | first_flag, r.t, pid, 0, e.pos, 0, e.occ, 0);
+    first_flag = 0;
+    r.n_disp++;
+  }
+  const uint32_t nid = r.next_id, nid2 = r.next_id + 1;  // uuid1 ×2 :340-341
+  r.next_id += 2;
+  const uint32_t parent = X.cellid[e.cell];
+  __syncwarp();
+  if (!driver) {  // :351-363 / :477-490
+    log_row(X, r, JSB_EV_DUPLICATE, first_flag, r.t, nid, parent, e.cell, 0, sp, 0);
+    log_row(X, r, JSB_EV_DUPLICATE, 0, r.t, nid2, parent, e.pos, 0, sp, 0);
+    if (X.lane == 0) {
+      X.cellid[e.cell] = nid;
+      X.cellid[e.pos] = nid2;
+      X.clone[e.pos] = (uint16_t)sp;
+    }
+    __syncwarp();
+    if (!list_append(X, r, sp - 1, e.pos)) return false;
+  } else {
+    uint32_t label;
+    double nalpha;
+    if (P.method == JSB_METHOD_TREE) {
+      label = (uint32_t)child_node + 1;
+      nalpha = X.node_rate[child_node];  // :503-505
+    } else {
+      uint32_t n_free = 1000u - (r.S);  // one label per clone, founder uses label 1
+      uint64_t a, b;
+      draw_block(X.key, r.it, 0, DS_LABEL, 0, a, b);
+      uint32_t j = bounded(X.key, a, n_free, r.it, DS_LABEL, 0, 0);  // :371
+      label = pick_label(r, j, X.lane);
+      double z = contract_randn(X, r.it);  // :565-566
+      nalpha = X.c_alpha[sp - 1] + fabs(P.adv_mean + P.adv_std * z);
+    }
+    const uint32_t nsp = r.S + 1;
+    const bool coin = u01_53(wb) < 0.5;  // :391 / :512
+    log_row(X, r, JSB_EV_MUTATION, first_flag, r.t, nid2, parent, coin ? e.pos : e.cell, 0, nsp, label);
+    log_row(X, r, JSB_EV_DUPLICATE, 0, r.t, nid, parent, coin ? e.cell : e.pos, 0, sp, 0);
+    if (coin) {  // :392-400
+      if (X.lane == 0) {
+        X.cellid[e.cell] = nid;
+        X.cellid[e.pos] = nid2;
+        X.clone[e.pos] = (uint16_t)nsp;
+      }
+      __syncwarp();
+      if (!new_clone(X, r, sp, label, nalpha, e.pos)) return false;
+    } else {  // :402-412
+      if (X.lane == 0) {
+        X.cellid[e.pos] = nid;
+        X.clone[e.pos] = (uint16_t)sp;
+        X.cellid[e.cell] = nid2;
+        X.clone[e.cell] = (uint16_t)nsp;
+      }
+      __syncwarp();
+      if (!list_append(X, r, sp - 1, e.pos)) return false;
+      list_remove_value(X, sp - 1, e.cell);
+      if (!new_clone(X, r, sp, label, nalpha, e.cell)) return false;
+    }
+  }
+  if (e.occ == 0) {  // :803-806
+    if (X.lane == 0) X.Alist[r.n] = e.pos;
+    __syncwarp();
+    r.n += 1;
+  }
+  r.n_eff++;
+  r.n_births++;
+  return true;
+}
+
+// Excision block :813-838 / :1036-1061: StatsBase.sample(rng, cs_alive, k; replace=false), then
+// cell_death for each sampled vertex in sample order, logged at time tb.
+__device__ void apply_excision(Ctx& X, Rep& r, double tb, double ratio) {
+  const uint32_t n = r.n;
+  const double taked = (double)n * ratio;  // :819
+  long long kk = (long long)trunc(taked);
+  if (kk < 0) kk = 0;
+  if (kk > (long long)n) kk = (long long)n;  // reference: sample() throws
+  const uint32_t k = (uint32_t)kk;
+  uint32_t* inds = X.inds;
+  uint32_t* samp = X.samp;
+  const int lane = X.lane;
+  if (k == 1) {
+    uint64_t a, b;
+    draw_block(X.key, r.it, 0, DS_EXCISION, 0, a, b);
+    uint32_t i = bounded(X.key, a, n, r.it, DS_EXCISION, 0, 0);
+    if (lane == 0) samp[0] = X.Alist[i];
+  } else if (k == 2) {  // samplepair
+    uint64_t a, b;
+    draw_block(X.key, r.it, 0, DS_EXCISION, 0, a, b);
+    uint32_t i1 = bounded(X.key, a, n, r.it, DS_EXCISION, 0, 0) + 1;
+    draw_block(X.key, r.it, 0, DS_EXCISION, 1, a, b);
+    uint32_t i2 = bounded(X.key, a, n - 1, r.it, DS_EXCISION, 1, 0) + 1;
+    if (lane == 0) {
+      samp[0] = X.Alist[i1 - 1];
+      samp[1] = X.Alist[(i2 == i1 ? n : i2) - 1];
+    }
+  } else if (k > 2 && (unsigned long long)n < (unsigned long long)k * 24ull) {  // fisher_yates_sample!
+    for (uint32_t i = lane; i < n; i += 32) inds[i] = i;
+    __syncwarp();
+    for (uint32_t base = 0; base < k; base += 32) {
+      uint32_t i = base + lane;
+      uint32_t jmine = 0;
+      if (i < k) {
+        uint64_t a, b;
+        draw_block(X.key, r.it, 0, DS_EXCISION, i, a, b);
+        jmine = i + bounded(X.key, a, n - i, r.it, DS_EXCISION, i, 0);  // rand(i:n)
+      }
+      uint32_t cnt = (k - base) < 32u ? (k - base) : 32u;
+      for (uint32_t l = 0; l < cnt; ++l) {  // the swaps are sequential
+        uint32_t j = __shfl_sync(FULL, jmine, (int)l);
+        if (lane == 0) {
+          uint32_t ii = base + l;
+          uint32_t tj = inds[j], ti = inds[ii];
+          inds[j] = ti;
+          inds[ii] = tj;
+          samp[ii] = X.Alist[tj];
+        }
+      }
+      __syncwarp();
+    }
+  } else if (k > 2) {  // self_avoid_sample!
+    for (uint32_t i = lane; i < n; i += 32) inds[i] = 0;
+    __syncwarp();
+    if (lane == 0) {
+      uint32_t q = 0;
+      for (uint32_t i = 0; i < k; ++i) {
+        uint32_t idx;
+        for (;;) {
+          uint64_t a, b;
+          draw_block(X.key, r.it, 0, DS_EXCISION, q, a, b);
+          idx = bounded(X.key, a, n, r.it, DS_EXCISION, q, 0);
+          ++q;
+          if (!inds[idx]) break;
+        }
+        inds[idx] = 1;
+        samp[i] = X.Alist[idx];
+      }
+    }
+  }
+  __syncwarp();
+  // deaths in sample order; rows written in parallel inside each log chunk
+  uint32_t done = 0;
+  while (done < k) {
+    uint32_t m = k - done;
+    if (r.log_on) {
+      uint32_t slot = (uint32_t)(r.nlog % kLogChunk);
+      if (slot == 0) log_open_chunk(X, r);
+      uint32_t room = kLogChunk - slot;
+      if (m > room) m = room;
+    }
+    for (uint32_t b = 0; b < m; b += 32) {
+      uint32_t i = b + lane;
+      if (i < m) {
+        uint32_t site = samp[done + i];
+        uint32_t cid = X.cellid[site];
+        uint32_t cl = X.clone[site];
+        if (r.log_on) {
+          jsb_event* dst = X.A->log_pool + (size_t)r.cur_chunk * kLogChunk + (uint32_t)(r.nlog % kLogChunk) + i;
+          uint32_t fl = JSB_EVF_EXCISION | ((done + i) == 0 ? JSB_EVF_GROUP_START : 0);
+          log_store(dst, 0, tb, cid, 0, site + 1, 0, cl, 0, JSB_EV_DEATH, fl);
+          log_store(dst, 1, tb, cid, 0, site + 1, 0, cl, 0, JSB_EV_DEATH, fl);
+        }
+      }
+    }
+    r.nlog += m;
+    done += m;
+  }
+  __syncwarp();
+  for (uint32_t i = lane; i < k; i += 32) X.clone[samp[i]] = 0;
+  __syncwarp();
+  // stable compaction of cs_alive and of every ca_subpop list (== the sequence of filter! calls)
+  {
+    uint32_t wpos = 0;
+    for (uint32_t base = 0; base < n; base += 32) {
+      uint32_t i = base + lane;
+      uint32_t v = 0;
+      bool keep = false;
+      if (i < n) { v = X.Alist[i]; keep = X.clone[v] != 0; }
+      uint32_t m = __ballot_sync(FULL, keep);
+      if (keep) X.Alist[wpos + __popc(m & ((1u << lane) - 1u))] = v;
+      wpos += __popc(m);
+      __syncwarp();
+    }
+  }
+  for (uint32_t c = 0; c < r.S; ++c) {
+    uint32_t len = X.c_len[c];
+    uint32_t* list = X.arena + X.c_off[c];
+    uint32_t wpos = 0;
+    for (uint32_t base = 0; base < len; base += 32) {
+      uint32_t i = base + lane;
+      uint32_t v = 0;
+      bool keep = false;
+      if (i < len) { v = list[i]; keep = X.clone[v] != 0; }
+      uint32_t m = __ballot_sync(FULL, keep);
+      if (keep) list[wpos + __popc(m & ((1u << lane) - 1u))] = v;
+      wpos += __popc(m);
+      __syncwarp();
+    }
+    if (lane == 0) X.c_len[c] = wpos;
+  }
+  __syncwarp();
+  r.n = n - k;
+  r.n_exc += k;
+  r.n_eff++;  // one series push :835-836
+}
+
+// ---------------------------------------------------------------------------------------------
+// Seeding: initialize_graph :79-163 and the initial lists :655-683
+// ---------------------------------------------------------------------------------------------
+__device__ void seed_replicate(Ctx& X, Rep& r) {
+  const DevPoint& P = *X.P;
+  const DevGraph& g = X.A->g;
+  const int lane = X.lane;
+  for (uint32_t i = lane; i < (g.nv + 1) / 2; i += 32) reinterpret_cast<uint32_t*>(X.clone)[i] = 0;
+  __syncwarp();
+  uint32_t n0 = 0;
+  if (P.n_start == 1) {
+    if (X.A->n_cand > 0) {
+      uint32_t j = 0;
+      if (X.A->n_cand > 1) {
+        uint64_t a, b;
+        draw_block(X.key, 0, 0, DS_SEED_TIE, 0, a, b);
+        j = bounded(X.key, a, X.A->n_cand, 0, DS_SEED_TIE, 0, 0);  // :86
+      }
+      uint32_t v0 = X.A->seed_cand[j];
+      if (lane == 0) {
+        X.clone[v0] = 1;
+        X.cellid[v0] = 1;
+        X.Alist[0] = v0;
+      }
+      n0 = 1;
+    }
+  } else if (P.n_start > 1) {
+    // :105-112 / :151-157: the i-th cell takes the j-th smallest remaining vertex; ids in draw
+    // order, lists in ascending vertex order.  samp[] holds the chosen vertices sorted.
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int i = 0; i < P.n_start; ++i) {
+        uint64_t a, b;
+        draw_block(X.key, 0, 0, DS_SEED_POS, (uint32_t)i, a, b);
+        uint32_t pos = bounded(X.key, a, g.nv - (uint32_t)i, 0, DS_SEED_POS, (uint32_t)i, 0);  // 0-based rank
+        uint32_t ins = 0;
+        for (uint32_t q = 0; q < cnt; ++q)
+          if (X.samp[q] <= pos) { ++pos; ins = q + 1; }
+        for (uint32_t q = cnt; q > ins; --q) X.samp[q] = X.samp[q - 1];
+        X.samp[ins] = pos;
+        ++cnt;
+        X.clone[pos] = 1;
+        X.cellid[pos] = (uint32_t)i + 1;
+      }
+      for (uint32_t q = 0; q < cnt; ++q) X.Alist[q] = X.samp[q];
+    }
+    n0 = (uint32_t)P.n_start;
+  }
+  __syncwarp();
+  r.n = n0;
+  r.next_id = n0 + 1;
+  r.S = 0;
+  r.arena_top = 0;
+  r.used_w = 0;
+  if (lane == 0) r.used_w = 0x3u;               // label 0 does not exist, label 1 is the founder
+  if (lane == 31) r.used_w = 0xFFFFFE00u;       // labels 1001..1023 do not exist
+  if (n0 > 0) {
+    uint32_t cap = kMinListCap;
+    while (cap < n0) cap *= 2;
+    if (lane == 0) {
+      X.c_off[0] = 0;
+      X.c_len[0] = n0;
+      X.c_cap[0] = cap;
+      X.c_alpha[0] = (P.method == JSB_METHOD_TREE) ? P.root_rate : P.rate_birth;  // :664 / :881
+      X.c_parent[0] = 0;
+      X.c_label[0] = (P.method == JSB_METHOD_TREE) ? (uint16_t)(P.root_node + 1) : (uint16_t)1;
+    }
+    for (uint32_t i = lane; i < n0; i += 32) X.arena[i] = X.Alist[i];
+    r.arena_top = cap;
+    r.S = 1;
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// One replicate
+// ---------------------------------------------------------------------------------------------
+__device__ void run_replicate(Ctx& X) {
+  const RunArgs& A = *X.A;
+  const DevPoint& P = *X.P;
+  const int lane = X.lane;
+  Rep r;
+  r.t = 0.0; r.theta = 0.0; r.it = 0; r.nlog = 0; r.cur_chunk = 0;
+  r.bott_id = P.n_bott > 0 ? 1 : 0;  // :668-672
+  r.snap_idx = 0;
+  r.status = JSB_ST_OK;
+  r.n_eff = r.n_births = r.n_deaths = r.n_migr = r.n_disp = r.n_exc = 0;
+  r.log_on = (A.flags & JSB_OUT_EVENTS) != 0;
+  seed_replicate(X, r);
+
+  const bool intent = (P.quirks & JSB_QUIRK_EXCISION_INTENT) != 0;
+  const uint32_t width = (P.quirks & JSB_QUIRK_DEBUG_SERIAL) ? 1u : 32u;
+  const uint32_t wmask = width == 32 ? FULL : ((1u << width) - 1u);
+  const uint32_t nv = A.g.nv;
+  bool dirty = true;
+
+  for (;;) {
+    if (!(r.t < P.Tf && r.n > 0)) {  // loop test :687-688
+      if (P.rate_death == 0.0 && r.n == nv) r.status = JSB_ST_NONTERMINATING;
+      break;
+    }
+    if (dirty) { rebuild_classes(X, r); dirty = false; }
+
+    // ---- 32 iterations' worth of draws -------------------------------------------------------
+    const uint64_t q = r.it + 1 + (uint64_t)lane;
+    uint64_t wa, wb, wc, wd;
+    draw_block(X.key, q, 0, DS_TIME_CLASS, 0, wa, wb);
+    draw_block(X.key, q, 0, DS_CELL_NBR, 0, wc, wd);
+    const double dt = (-contract_log(u01_open(wa))) * r.theta;  // :699
+    Eval e = evaluate(X, r, q, wb, wc, wd);
+    const uint32_t effmask = __ballot_sync(FULL, e.effective) & wmask;
+    const uint32_t jE = effmask ? (uint32_t)__ffs(effmask) - 1u : width - 1u;
+
+    // ---- time chain over the lanes that may commit --------------------------------------------
+    double tend = r.t;
+    for (uint32_t l = 0; l <= jE; ++l) tend = tend + __shfl_sync(FULL, dt, (int)l);  // :701
+
+    // ---- can anything other than the event at jE happen in (t, tend]? --------------------------
+    bool slow = !(tend < P.Tf);
+    if (P.max_iter && r.it + jE + 1 > P.max_iter) slow = true;
+    if (r.snap_idx < P.n_snap && tend > X.tsnap[r.snap_idx]) slow = true;
+    if (P.n_bott > 0) {
+      if (intent) {
+        if (r.bott_id > 0) { double tb = X.tb[r.bott_id - 1]; if (tb > r.t && tb <= tend) slow = true; }
+      } else if (P.method == JSB_METHOD_TREE) {
+        if (r.it + 1 < (uint64_t)P.n_bott) slow = true;
+        else { double tb = X.tb[P.n_bott - 1]; if (tb > r.t && tb <= tend) slow = true; }
+      } else {
+        double tb = X.tb[0]; if (tb > r.t && tb <= tend) slow = true;
+      }
+    }
+
+    uint32_t j = jE;
+    bool do_event = effmask != 0;
+    bool do_snap = false, do_bott = false;
+    double tb_fire = 0.0, ratio_fire = 0.0;
+    double t_old = r.t;
+
+    if (!slow) {
+      r.it += jE + 1;
+      r.t = tend;
+    } else {
+      // per-lane (t_old, t_curr) of every candidate iteration
+      double my_prev = r.t, my_t = r.t, run = r.t;
+      for (uint32_t l = 0; l <= jE; ++l) {
+        double prev = run;
+        run = run + __shfl_sync(FULL, dt, (int)l);
+        if ((uint32_t)lane == l) { my_prev = prev; my_t = run; }
+      }
+      const bool in_range = (uint32_t)lane <= jE;
+      const bool stop_l = in_range && !(my_prev < P.Tf);
+      const bool maxit_l = in_range && P.max_iter && (r.it + (uint64_t)lane >= P.max_iter);
+      bool bott_l = false;
+      double tb_l = 0.0, ratio_l = 0.0;
+      if (in_range && P.n_bott > 0) {
+        int id = 0;
+        if (intent) id = r.bott_id;
+        else if (P.method == JSB_METHOD_TREE) id = (int)(q < (uint64_t)P.n_bott ? q : (uint64_t)P.n_bott);  // :1062-1064
+        else id = 1;  // method 1 never advances id_bottleneck
+        if (id > 0) {
+          tb_l = X.tb[id - 1];
+          ratio_l = X.ratio[id - 1];
+          bott_l = tb_l > my_prev && tb_l <= my_t;  // :814-815
+        }
+      }
+      const bool snap_l = in_range && r.snap_idx < P.n_snap && my_t > X.tsnap[r.snap_idx];  // :708-710
+      const bool special = stop_l || maxit_l || bott_l || snap_l || (in_range && e.effective);
+      const uint32_t smask = __ballot_sync(FULL, special) & wmask;
+      if (smask == 0) {  // cannot happen when slow was triggered by tend >= Tf etc. but be safe
+        r.it += jE + 1;
+        r.t = tend;
+        continue;
+      }
+      j = (uint32_t)__ffs(smask) - 1u;
+      const bool stop_j = __shfl_sync(FULL, (int)stop_l, (int)j) != 0;
+      const bool maxit_j = __shfl_sync(FULL, (int)maxit_l, (int)j) != 0;
+      const double prev_j = __shfl_sync(FULL, my_prev, (int)j);
+      const double t_j = __shfl_sync(FULL, my_t, (int)j);
+      if (stop_j || maxit_j) {
+        r.it += j;
+        r.t = prev_j;
+        if (stop_j) { if (P.rate_death == 0.0 && r.n == nv) r.status = JSB_ST_NONTERMINATING; }
+        else r.status = JSB_ST_MAX_ITER;
+        break;
+      }
+      r.it += j + 1;
+      t_old = prev_j;
+      r.t = t_j;
+      do_event = __shfl_sync(FULL, (int)e.effective, (int)j) != 0;
+      do_snap = __shfl_sync(FULL, (int)snap_l, (int)j) != 0;
+      do_bott = __shfl_sync(FULL, (int)bott_l, (int)j) != 0;
+      tb_fire = __shfl_sync(FULL, tb_l, (int)j);
+      ratio_fire = __shfl_sync(FULL, ratio_l, (int)j);
+    }
+    (void)t_old;
+
+    if (do_snap) {  // :708-714
+      if (lane == 0 && A.snaps) {
+        jsb_snapshot s;
+        s.time = r.t; s.iteration = r.it; s.n_events_before = r.nlog; s.n_alive = r.n;
+        s.index = (uint32_t)r.snap_idx;
+        A.snaps[(size_t)X.local_idx * A.max_snap + r.snap_idx] = s;
+      }
+      r.snap_idx++;
+    }
+    bool keep_going = true;
+    if (do_event) {
+      Eval ej;
+      ej.cls = __shfl_sync(FULL, e.cls, (int)j);
+      ej.x = __shfl_sync(FULL, e.x, (int)j);
+      ej.cell = __shfl_sync(FULL, e.cell, (int)j);
+      ej.pos = __shfl_sync(FULL, e.pos, (int)j);
+      ej.occ = __shfl_sync(FULL, e.occ, (int)j);
+      ej.effective = true;
+      if (ej.cls == r.S + 1) apply_migration(X, r, ej);
+      else if (ej.cls == r.S) { apply_death(X, r, ej); dirty = true; }
+      else { keep_going = apply_birth(X, r, ej); dirty = true; }
+    }
+    if (!keep_going) break;
+    if (do_bott) {
+      apply_excision(X, r, tb_fire, ratio_fire);
+      dirty = true;
+      if (intent) r.bott_id = (r.bott_id < P.n_bott) ? r.bott_id + 1 : 0;
+    }
+    if (r.status == JSB_ST_INTERNAL) break;
+  }
+
+  // ---- outputs --------------------------------------------------------------------------------
+  __syncwarp();
+  if (lane == 0) {
+    jsb_summary s;
+    s.n_iterations = r.it;
+    s.n_events = r.nlog;
+    s.t_final = r.t;
+    s.n_effective = r.n_eff;
+    s.n_births = r.n_births;
+    s.n_deaths = r.n_deaths;
+    s.n_migrations = r.n_migr;
+    s.n_displaced = r.n_disp;
+    s.n_excised = r.n_exc;
+    s.n_alive = r.n;
+    s.n_clones = r.S;
+    s.next_cell_id = r.next_id;
+    s.status = r.status;
+    A.summaries[X.local_idx] = s;
+  }
+  // clone table
+  long long off = -1;
+  if (A.clone_pool) {
+    unsigned long long o = 0;
+    if (lane == 0) o = atomicAdd(A.clone_pool_next, (unsigned long long)r.S);
+    o = __shfl_sync(FULL, o, 0);
+    if (o + r.S <= A.clone_pool_cap) {
+      off = (long long)o;
+      for (uint32_t i = lane; i < r.S; i += 32) {
+        jsb_clone c;
+        c.alpha = X.c_alpha[i];
+        c.count = X.c_len[i];
+        c.parent = X.c_parent[i];
+        c.label = X.c_label[i];
+        A.clone_pool[o + i] = c;
+      }
+    }
+    if (lane == 0) A.clone_off[X.local_idx] = off;
+  }
+  if (A.out_clone) {
+    uint16_t* oc = A.out_clone + (size_t)X.local_idx * nv;
+    uint32_t* oi = A.out_cell + (size_t)X.local_idx * nv;
+    for (uint32_t v = lane; v < nv; v += 32) {
+      uint16_t cl = X.clone[v];
+      oc[v] = cl;
+      oi[v] = cl ? X.cellid[v] : 0u;
+    }
+  }
+  if (A.out_lists) {
+    uint32_t* la = A.out_lists + (size_t)X.local_idx * 2 * nv;
+    uint32_t* ll = la + nv;
+    for (uint32_t i = lane; i < r.n; i += 32) la[i] = X.Alist[i] + 1;
+    uint32_t wpos = 0;
+    for (uint32_t c = 0; c < r.S; ++c) {
+      uint32_t len = X.c_len[c];
+      const uint32_t* list = X.arena + X.c_off[c];
+      for (uint32_t i = lane; i < len; i += 32) ll[wpos + i] = list[i] + 1;
+      wpos += len;
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) ssa_kernel(const __grid_constant__ RunArgs A) {
+  __shared__ double s_tab[kWarpsPerBlock][2][kSmemClasses];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint64_t slot = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const WsLayout L = ws_layout(A.g.nv, A.arena_cap);
+  uint8_t* base = A.ws + slot * A.ws_stride;
+  Ctx X;
+  X.A = &A;
+  X.lane = lane;
+  X.clone = reinterpret_cast<uint16_t*>(base + L.clone);
+  X.cellid = reinterpret_cast<uint32_t*>(base + L.cellid);
+  X.Alist = reinterpret_cast<uint32_t*>(base + L.A);
+  X.arena = reinterpret_cast<uint32_t*>(base + L.arena);
+  X.inds = reinterpret_cast<uint32_t*>(base + L.inds);
+  X.samp = reinterpret_cast<uint32_t*>(base + L.samp);
+  X.c_off = reinterpret_cast<uint32_t*>(base + L.c_off);
+  X.c_len = reinterpret_cast<uint32_t*>(base + L.c_len);
+  X.c_cap = reinterpret_cast<uint32_t*>(base + L.c_cap);
+  X.c_alpha = reinterpret_cast<double*>(base + L.c_alpha);
+  X.c_parent = reinterpret_cast<uint16_t*>(base + L.c_parent);
+  X.c_label = reinterpret_cast<uint16_t*>(base + L.c_label);
+  X.g_w = reinterpret_cast<double*>(base + L.g_w);
+  X.g_c = reinterpret_cast<double*>(base + L.g_c);
+  X.s_w = s_tab[warp][0];
+  X.s_c = s_tab[warp][1];
+  X.w = X.s_w;
+  X.c = X.s_c;
+  X.key.k0 = (uint32_t)A.seed;
+  X.key.k1 = (uint32_t)(A.seed >> 32);
+
+  for (;;) {
+    unsigned long long idx = 0;
+    if (lane == 0) idx = atomicAdd(A.work_counter, 1ull);
+    idx = __shfl_sync(FULL, idx, 0);
+    if ((long long)idx >= A.n_local) break;
+    const int64_t gidx = A.g_begin + (int64_t)idx;
+    X.local_idx = (int64_t)idx;
+    X.key.stream = (uint32_t)gidx;
+    const DevPoint* P = A.points + (gidx / A.reps_per_point);
+    X.P = P;
+    X.tb = A.dpool + P->bott_off;
+    X.ratio = X.tb + P->n_bott;
+    X.tsnap = A.dpool + P->snap_off;
+    X.node_rate = A.dpool + P->rate_off;
+    X.edge_parent = A.ipool + P->edge_off;
+    X.edge_child = X.edge_parent + P->n_edges;
+    run_replicate(X);
+  }
+}
+
+int launch_ssa(const RunArgs& args, int grid_blocks, void* stream) {
+  ssa_kernel<<<grid_blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(args);
+  return (int)cudaGetLastError();
+}
+
+int ssa_max_blocks_per_sm() {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ssa_kernel, kWarpsPerBlock * 32, 0);
+  return nb;
+}
+
+size_t ssa_smem_bytes() { return sizeof(double) * kWarpsPerBlock * 2 * kSmemClasses; }
+
+}  // namespace jsb

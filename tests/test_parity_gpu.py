@@ -1,0 +1,124 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle, bit-exact, on seeded inputs at
+sizes the oracle finishes in seconds.  Integer fields (cell ids, parents, sites, clones, labels,
+event types) must be identical; fp64 times and fitness values are required to be identical too
+(the north-star tolerance is 1e-12 relative; we hold the stricter bar because both sides
+implement the same IEEE expression order)."""
+import os
+
+import numpy as np
+import pytest
+
+from parity import TREE_EDGES, TREE_RATES, compare_runs
+
+pytestmark = pytest.mark.gpu
+
+DEFAULT = dict(Tf=60.0, rate_birth=0.2, rate_death=0.01, rate_migration=0.01, mu_driver=0.01,
+               adv_mean=0.4, adv_std=0.1, rule="contact")
+TREE = dict(method=2, Tf=80.0, rate_death=0.01, rate_migration=0.01, mu_driver=0.05, rule="contact",
+            tree_edges=TREE_EDGES, node_rate=TREE_RATES, root_node=0, root_rate=0.2)
+
+
+def test_contact_2d_default(jsb, oracle):
+    s = compare_runs(jsb, oracle, ("lattice", 2, 40, 40), DEFAULT, reps=8)
+    assert sum(int(x["n_births"]) for x in s) > 1000
+
+
+def test_c1_100x100_full_run(jsb, oracle):
+    # BASELINE config 1: 100x100, Parameters.toml dynamics, one excision
+    p = dict(DEFAULT, Tf=200.0, t_bottleneck=[50.0], ratio_bottleneck=[0.8])
+    s = compare_runs(jsb, oracle, ("lattice", 2, 100, 100), p, reps=2)
+    assert max(int(x["n_clones"]) for x in s) > 30
+
+
+@pytest.mark.parametrize("rule", ["voter", "hvoter", "anything-else"])
+def test_rules(jsb, oracle, rule):
+    p = dict(DEFAULT, rule=rule, Tf=40.0 if rule != "contact" else 60.0, mu_driver=0.05)
+    compare_runs(jsb, oracle, ("lattice", 2, 24, 24), p, reps=6)
+
+
+def test_serial_debug_path_matches(jsb, oracle):
+    from jspace_b200 import _lib as L
+    p = dict(DEFAULT, Tf=45.0, quirk_flags=L.QUIRK_DEBUG_SERIAL)
+    compare_runs(jsb, oracle, ("lattice", 2, 30, 30), p, reps=4)
+
+
+def test_3d_tree_excision(jsb, oracle):
+    # BASELINE config 3 at reduced size: 3D cube, driver tree, hvoter and contact, one excision
+    for rule in ("contact", "hvoter"):
+        p = dict(TREE, rule=rule, t_bottleneck=[40.0], ratio_bottleneck=[0.8])
+        compare_runs(jsb, oracle, ("lattice", 3, 30, 30), p, reps=4)
+
+
+def test_excision_branches_and_quirks(jsb, oracle):
+    from jspace_b200 import _lib as L
+    base = dict(DEFAULT, Tf=70.0)
+    # two excisions: reference method 1 only fires the first; intent mode fires both
+    compare_runs(jsb, oracle, ("lattice", 2, 32, 32), dict(base, t_bottleneck=[30.0, 50.0], ratio_bottleneck=[0.5, 0.9]), reps=3)
+    compare_runs(jsb, oracle, ("lattice", 2, 32, 32), dict(base, t_bottleneck=[30.0, 50.0], ratio_bottleneck=[0.5, 0.9],
+                                                          quirk_flags=L.QUIRK_EXCISION_INTENT), reps=3)
+    # small ratios reach StatsBase's k == 1, k == 2 and self-avoid branches
+    seen = set()
+    for ratio in (0.01, 0.02, 0.03, 0.05, 0.0):
+        out = compare_runs(jsb, oracle, ("lattice", 2, 32, 32), dict(base, t_bottleneck=[60.0], ratio_bottleneck=[ratio]), reps=6)
+        seen |= {int(x["n_excised"]) for x in out}
+    assert {0, 1, 2} <= seen and max(seen) >= 3
+    # method 2 advances the excision index every iteration (only the last entry can fire late)
+    compare_runs(jsb, oracle, ("lattice", 2, 32, 32), dict(TREE, t_bottleneck=[20.0, 45.0], ratio_bottleneck=[0.5, 0.7]), reps=3)
+    compare_runs(jsb, oracle, ("lattice", 2, 32, 32), dict(TREE, t_bottleneck=[20.0, 45.0], ratio_bottleneck=[0.5, 0.7],
+                                                          quirk_flags=L.QUIRK_EXCISION_INTENT), reps=3)
+
+
+def test_snapshots_and_multi_seed_cells(jsb, oracle):
+    p = dict(DEFAULT, Tf=50.0, t_snapshot=[10.0, 20.0, 49.0, 500.0], n_start_cells=5)
+    compare_runs(jsb, oracle, ("lattice", 2, 30, 30), p, reps=4)
+
+
+def test_empty_and_degenerate_inputs(jsb, oracle):
+    compare_runs(jsb, oracle, ("lattice", 2, 10, 10), dict(DEFAULT, n_start_cells=0), reps=2)
+    compare_runs(jsb, oracle, ("lattice", 2, 1, 1), dict(DEFAULT), reps=2)          # single site
+    compare_runs(jsb, oracle, ("lattice", 2, 1, 7), dict(DEFAULT, Tf=100.0), reps=3)  # a path
+    compare_runs(jsb, oracle, ("lattice", 2, 6, 6), dict(DEFAULT, Tf=0.0), reps=1)  # loop never entered
+    # rate_death == 0 on a lattice that fills: the reference loop never exits -> flagged
+    s = compare_runs(jsb, oracle, ("lattice", 2, 5, 5), dict(DEFAULT, rate_death=0.0, Tf=400.0), reps=2)
+    assert all(int(x["status"]) == 1 for x in s)
+    s = compare_runs(jsb, oracle, ("lattice", 2, 12, 12), dict(DEFAULT, max_iterations=777), reps=2)
+    assert any(int(x["status"]) == 4 for x in s)
+
+
+def test_adjacency_graph(jsb, oracle):
+    path = os.path.join(os.path.dirname(__file__), "golden", "Example_adj_matrix.txt")
+    compare_runs(jsb, oracle, ("dense", path), dict(DEFAULT, Tf=100.0, rate_death=0.05), reps=8)
+
+
+def test_random_geometric_graph_csr(jsb, oracle):
+    # BASELINE config 4 at reduced size
+    from graphs import random_geometric_csr
+    rowptr, colidx = random_geometric_csr(3000, seed=4321)
+    compare_runs(jsb, oracle, ("csr", rowptr, colidx), dict(DEFAULT, Tf=80.0), reps=4, candidates=[17])
+
+
+def test_stream_offset_equals_sharding(jsb, oracle):
+    # replicate g uses stream g wherever it runs: a shard starting at g=5 reproduces streams 5..8
+    compare_runs(jsb, oracle, ("lattice", 2, 24, 24), dict(DEFAULT, Tf=40.0), reps=4, g_begin=5)
+
+
+def test_many_clones_global_class_table(jsb, oracle):
+    # > 126 clones pushes the class table out of shared memory and through the pairwise cumsum
+    p = dict(DEFAULT, Tf=130.0, mu_driver=0.2, adv_mean=0.02, adv_std=0.01)
+    s = compare_runs(jsb, oracle, ("lattice", 2, 40, 40), p, reps=2)
+    assert max(int(x["n_clones"]) for x in s) > 257  # at least one pairwise split of the cumsum
+
+
+def test_arena_compaction(jsb, oracle, monkeypatch):
+    # voter turnover with a minimal list arena forces in-place compactions
+    monkeypatch.setenv("JSB_DEBUG_ARENA_ENTRIES", "12000")
+    p = dict(DEFAULT, rule="voter", Tf=150.0, mu_driver=0.01, rate_death=0.05)
+    s = compare_runs(jsb, oracle, ("lattice", 2, 20, 20), p, reps=2)
+    assert max(int(x["n_clones"]) for x in s) > 100 and all(int(x["status"]) == 0 for x in s)
+
+
+def test_clone_capacity_stop(jsb, oracle):
+    # 1000 clones = every label of Set(1:1000) used: the reference throws at :371; both sides stop
+    p = dict(DEFAULT, rule="voter", Tf=150.0, mu_driver=0.1, rate_death=0.05)
+    s = compare_runs(jsb, oracle, ("lattice", 2, 20, 20), p, reps=1)
+    assert int(s[0]["status"]) == 2 and int(s[0]["n_clones"]) == 1000
