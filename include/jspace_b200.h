@@ -57,6 +57,11 @@ extern "C" {
 /* Test hook: evaluate every iteration through the one-at-a-time path instead of the
  * speculative 32-iteration batch.  Results must be identical.                              */
 #define JSB_QUIRK_DEBUG_SERIAL 0x100u
+/* Test hooks for the event-class selection: always use the exact prob_cum
+ * table / widen the guard band to 1e-3 so the exact fallback runs constantly.  Results must be
+ * identical.                                                                               */
+#define JSB_QUIRK_DEBUG_EXACT_CLASSES 0x200u
+#define JSB_QUIRK_DEBUG_WIDE_GUARD 0x400u
 
 /* ---- output selection (jsb_run_opts.flags) -------------------------------------------- */
 #define JSB_OUT_EVENTS 0x1u  /* keep the per-replicate event log (`df`)                   */

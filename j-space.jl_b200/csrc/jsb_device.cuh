@@ -8,7 +8,8 @@ namespace jsb {
 
 constexpr int kMaxClones = 1000;   // Set(1:1000), src/J_Space.jl:366
 constexpr int kTab = 1024;         // clone-table stride
-constexpr int kSmemClasses = 128;  // event classes (S+2) whose tables fit the per-warp smem slice
+constexpr int kSmemTable = 512;    // class boundaries (S+2) kept in the per-warp smem slice
+constexpr double kGuardEps = 1e-11; // class-selection guard band (relative to λ), DESIGN.md §4
 constexpr int kLogChunk = 1024;    // records per event-log chunk (32 KB)
 constexpr int kMinListCap = 32;    // initial capacity of a ca_subpop list in the arena
 constexpr int kWarpsPerBlock = 4;
@@ -61,6 +62,7 @@ struct RunArgs {
   uint8_t* ws;
   uint64_t ws_stride;
   uint32_t arena_cap;  // entries
+  uint32_t site_bytes; // 2 when nv <= 65536, else 4 (storage type of the ordered lists)
   // outputs
   jsb_summary* summaries;
   jsb_clone* clone_pool;
@@ -82,17 +84,17 @@ struct RunArgs {
 
 // Workspace layout per slot (all offsets 16-byte aligned); computed identically on host and device.
 struct WsLayout {
-  uint64_t clone, cellid, A, arena, inds, samp, c_off, c_len, c_cap, c_alpha, c_parent, c_label, g_w, g_c,
+  uint64_t clone, cellid, A, arena, inds, samp, c_off, c_len, c_cap, c_alpha, c_parent, c_label, g_B, g_w, g_c,
       total;
 };
 __host__ __device__ inline uint64_t jsb_align16(uint64_t x) { return (x + 15) & ~uint64_t(15); }
-__host__ __device__ inline WsLayout ws_layout(uint32_t nv, uint32_t arena_cap) {
+__host__ __device__ inline WsLayout ws_layout(uint32_t nv, uint32_t arena_cap, uint32_t site_bytes) {
   WsLayout L;
   uint64_t o = 0;
   L.clone = o;    o = jsb_align16(o + 2ull * nv);
   L.cellid = o;   o = jsb_align16(o + 4ull * nv);
-  L.A = o;        o = jsb_align16(o + 4ull * (nv + 1));
-  L.arena = o;    o = jsb_align16(o + 4ull * arena_cap);
+  L.A = o;        o = jsb_align16(o + (uint64_t)site_bytes * (nv + 1) + 32);   // +32: vector-shift read slack
+  L.arena = o;    o = jsb_align16(o + (uint64_t)site_bytes * arena_cap + 32);
   L.inds = o;     o = jsb_align16(o + 4ull * nv);
   L.samp = o;     o = jsb_align16(o + 4ull * nv);
   L.c_off = o;    o = jsb_align16(o + 4ull * kTab);
@@ -101,6 +103,7 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t nv, uint32_t arena_cap) {
   L.c_alpha = o;  o = jsb_align16(o + 8ull * kTab);
   L.c_parent = o; o = jsb_align16(o + 2ull * kTab);
   L.c_label = o;  o = jsb_align16(o + 2ull * kTab);
+  L.g_B = o;      o = jsb_align16(o + 8ull * (kTab + 8));
   L.g_w = o;      o = jsb_align16(o + 8ull * (kTab + 8));
   L.g_c = o;      o = jsb_align16(o + 8ull * (kTab + 8));
   L.total = (o + 255) & ~uint64_t(255);

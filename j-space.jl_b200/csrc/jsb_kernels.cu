@@ -11,11 +11,19 @@
 //     change any state.  The warp therefore evaluates 32 consecutive iterations speculatively
 //     against the current state (class selection, member lookup, neighbour, occupancy test), finds
 //     the first lane whose iteration changes state (ballot + ffs), commits all earlier
-//     null iterations in one go, applies that one event cooperatively (parallel list shifts,
+//     null iterations in one go, applies that one event cooperatively (vectorised list shifts,
 //     searches, log stores) and re-speculates from the next iteration.
-//   * Event times are the only sequential fp64 chain (t += θ·e); it is run over the committed
-//     lanes only, and the per-lane times are materialised only when the batch may touch Tf, an
-//     excision time or a snapshot time.
+//   * Event times are a sequential fp64 chain (t += θ·e); it is run over the committed lanes
+//     only, and per-lane times are materialised only when the batch may touch Tf, an excision
+//     time or a snapshot time.
+//   * Event-class selection.  The reference recomputes, every iteration, w_i = α_i·n_i, their
+//     sequential sum, λ, the vector w/λ and its pairwise cumsum, then findfirst(k .<= prob_cum).
+//     Here the sequential prefix sums B_i = fl(B_{i-1} + w_i) are kept (they ARE the reference's
+//     `sum`, so λ and θ are bit-exact) and re-folded only from the first clone whose size changed.
+//     A class is selected by comparing k·λ with B_i; because |prob_cum_i − B_i/λ| < 4·(S+2)·2^-53,
+//     the choice is provably the reference's whenever k·λ is farther than ε·λ (ε = 1e-11) from
+//     both neighbouring boundaries.  Otherwise (≈ 1e-8 of iterations) the exact prob_cum table is
+//     built in the reference's order and used instead.
 // Everything that must match the reference bit-for-bit (sum order of Σα·n, the pairwise cumsum,
 // insertion-ordered lists with stable deletes) is kept in the reference's order; see DESIGN.md.
 //
@@ -30,6 +38,7 @@
 namespace jsb {
 
 #define FULL 0xffffffffu
+constexpr uint32_t kNone = 0xFFFFFFFFu;
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 and the draw contract
@@ -64,23 +73,28 @@ __device__ __forceinline__ void draw_block(const Key& key, uint64_t iter, uint32
   b = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
 }
 
+// Rejection branch of Lemire's bounded draw (probability s / 2^64 per draw): out of line.
+__device__ __noinline__ uint32_t bounded_retry(Key key, uint64_t lo, uint64_t hi, uint32_t s, uint64_t iter,
+                                               uint32_t site, uint32_t seq, int half) {
+  uint64_t t = (0ull - (uint64_t)s) % (uint64_t)s;
+  uint32_t attempt = 0;
+  while (lo < t) {
+    ++attempt;
+    uint64_t a, b;
+    draw_block(key, iter, attempt, site, seq, a, b);
+    uint64_t w = half ? b : a;
+    hi = __umul64hi(w, (uint64_t)s);
+    lo = w * (uint64_t)s;
+  }
+  return (uint32_t)hi;
+}
+
 // Lemire's nearly-divisionless bounded draw; `w` is attempt 0 of (iter, site, seq, half).
 __device__ __forceinline__ uint32_t bounded(const Key& key, uint64_t w, uint32_t s, uint64_t iter, uint32_t site,
                                             uint32_t seq, int half) {
   uint64_t hi = __umul64hi(w, (uint64_t)s);
   uint64_t lo = w * (uint64_t)s;
-  if (lo < (uint64_t)s) {  // probability s / 2^64
-    uint64_t t = (0ull - (uint64_t)s) % (uint64_t)s;
-    uint32_t attempt = 0;
-    while (lo < t) {
-      ++attempt;
-      uint64_t a, b;
-      draw_block(key, iter, attempt, site, seq, a, b);
-      w = half ? b : a;
-      hi = __umul64hi(w, (uint64_t)s);
-      lo = w * (uint64_t)s;
-    }
-  }
+  if (lo < (uint64_t)s) return bounded_retry(key, lo, hi, s, iter, site, seq, half);
   return (uint32_t)hi;
 }
 
@@ -131,50 +145,55 @@ __device__ __forceinline__ uint32_t lattice_pick(const DevGraph& g, uint32_t v, 
     bool here = ((mask >> b) & 1u) && (__popc(mask & ((1u << b) - 1u)) == (int)j);
     if (here) bit = b;
   }
-  uint32_t plane = g.n1 * g.n2;
-  switch (bit) {
-    case 0: return v - plane;
-    case 1: return v - g.n1;
-    case 2: return v - 1;
-    case 3: return v + 1;
-    case 4: return v + g.n1;
-    default: return v + plane;
-  }
+  const int plane = (int)(g.n1 * g.n2);
+  const int n1 = (int)g.n1;
+  int delta = bit == 0 ? -plane : bit == 1 ? -n1 : bit == 2 ? -1 : bit == 3 ? 1 : bit == 4 ? n1 : plane;
+  return (uint32_t)((int)v + delta);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-replicate context
+// Per-replicate context.  T = storage type of the ordered lists (uint16_t when nv <= 65536).
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 struct Ctx {
   const RunArgs* A;
   const DevPoint* P;
   const double *tb, *ratio, *tsnap, *node_rate;
   const int32_t *edge_parent, *edge_child;
   uint16_t* clone;
-  uint32_t *cellid, *Alist, *arena, *inds, *samp;
+  uint32_t* cellid;
+  T *Alist, *arena;
+  uint32_t *inds, *samp;
   uint32_t *c_off, *c_len, *c_cap;
   double* c_alpha;
   uint16_t *c_parent, *c_label;
-  double *g_w, *g_c, *s_w, *s_c;
-  double *w, *c;  // active class tables: shared slice while S+2 <= kSmemClasses, else global
+  double *g_B, *g_w, *g_c;  // global-memory tables (large S / exact fallback)
+  double *s_B, *s_w;        // per-warp shared slices: boundaries [kSmemTable], staging [32]
+  double* B;                // active boundary table: s_B while S+2 <= kSmemTable, else g_B
   Key key;
   int64_t local_idx;
   int lane;
 };
 
 struct Rep {
-  double t, theta;
+  double t, theta, lambda, guard;
   uint64_t it, nlog;
   uint32_t n, S, next_id, arena_top, cur_chunk, used_w;
+  uint32_t dirty_from;  // first clone index whose size changed since the last refold (kNone = clean)
   int bott_id, snap_idx, status;
   uint32_t n_eff, n_births, n_deaths, n_migr, n_disp, n_exc;
-  bool log_on;
+  bool log_on, exact_valid;
 };
+
+__device__ __forceinline__ void mark_dirty(Rep& r, uint32_t clone_idx) {
+  r.dirty_from = clone_idx < r.dirty_from ? clone_idx : r.dirty_from;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Event log: 32-byte records in pool chunks, rows in the reference's push! order
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool log_open_chunk(Ctx& X, Rep& r) {
+template <typename T>
+__device__ __noinline__ void log_open_chunk(Ctx<T>& X, Rep& r) {
   uint32_t c = 0;
   if (X.lane == 0) {
     c = atomicAdd(X.A->chunk_next, 1u);
@@ -187,40 +206,40 @@ __device__ __forceinline__ bool log_open_chunk(Ctx& X, Rep& r) {
   if (c >= X.A->n_chunks) {
     r.log_on = false;
     r.status = JSB_ST_LOG_OVERFLOW;
-    return false;
+    return;
   }
   r.cur_chunk = c;
-  return true;
 }
 
-__device__ __forceinline__ void log_store(jsb_event* dst, int lane_sel, double time, uint32_t cell, uint32_t parent,
-                                          uint32_t site, uint32_t site2, uint32_t clone, uint32_t label, uint32_t type,
-                                          uint32_t flags) {
+__device__ __forceinline__ void log_store(jsb_event* dst, int half, double time, uint32_t cell, uint32_t parent,
+                                          uint32_t site1, uint32_t site2, uint32_t clone, uint32_t label,
+                                          uint32_t type, uint32_t flags) {
   // two 16-byte stores = one full 32-byte sector
   uint4 v;
-  if (lane_sel == 0) {
+  if (half == 0) {
     v.x = (uint32_t)__double2loint(time);
     v.y = (uint32_t)__double2hiint(time);
     v.z = cell;
     v.w = parent;
   } else {
-    v.x = site;
+    v.x = site1;
     v.y = site2;
     v.z = (clone & 0xFFFFu) | (label << 16);
     v.w = (type & 0xFFu) | ((flags & 0xFFu) << 8);
   }
-  reinterpret_cast<uint4*>(dst)[lane_sel] = v;
+  reinterpret_cast<uint4*>(dst)[half] = v;
 }
 
-__device__ __forceinline__ void log_row(Ctx& X, Rep& r, uint32_t type, uint32_t flags, double time, uint32_t cell,
-                                        uint32_t parent, uint32_t site0, uint32_t site2_0, uint32_t clone,
+template <typename T>
+__device__ __forceinline__ void log_row(Ctx<T>& X, Rep& r, uint32_t type, uint32_t flags, double time, uint32_t cell,
+                                        uint32_t parent, uint32_t site0, uint32_t site2_1, uint32_t clone,
                                         uint32_t label) {
   if (r.log_on) {
     uint32_t slot = (uint32_t)(r.nlog % kLogChunk);
     if (slot == 0) log_open_chunk(X, r);
     if (r.log_on && X.lane < 2) {
       jsb_event* dst = X.A->log_pool + (size_t)r.cur_chunk * kLogChunk + slot;
-      log_store(dst, X.lane, time, cell, parent, site0 + 1, site2_0, clone, label, type, flags);
+      log_store(dst, X.lane, time, cell, parent, site0 + 1, site2_1, clone, label, type, flags);
     }
   }
   r.nlog++;
@@ -229,44 +248,124 @@ __device__ __forceinline__ void log_row(Ctx& X, Rep& r, uint32_t type, uint32_t 
 // ---------------------------------------------------------------------------------------------
 // Ordered lists.  cs_alive is one array; the ca_subpop lists live in an arena as contiguous
 // blocks (offset, len, cap) so that `list[x]` is a single load.  filter!(e -> e != v, list) is a
-// parallel search + left shift (stable).  Blocks grow by doubling; when the arena is exhausted
-// it is compacted in place (dead space squeezed out, order inside every list untouched).
+// vectorised search + left shift (stable): 16-byte loads, several in flight per lane.  Blocks
+// start on 16-byte boundaries and have capacities that are multiples of 16 bytes.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t list_find(const uint32_t* list, uint32_t len, uint32_t value, int lane) {
-  for (uint32_t base = 0; base < len; base += 32) {
-    uint32_t i = base + lane;
-    bool hit = (i < len) && (list[i] == value);
-    uint32_t m = __ballot_sync(FULL, hit);
-    if (m) return base + (uint32_t)__ffs(m) - 1u;
+template <typename T> struct Vec;
+template <> struct Vec<uint32_t> {
+  static constexpr uint32_t EPV = 4;
+  static __device__ __forceinline__ uint4 shift1(uint4 v, uint32_t nx) { return make_uint4(v.y, v.z, v.w, nx); }
+  static __device__ __forceinline__ uint32_t match(uint4 v, uint32_t value) {  // bitmask over the 4 elements
+    return (uint32_t)(v.x == value) | ((uint32_t)(v.y == value) << 1) | ((uint32_t)(v.z == value) << 2) |
+           ((uint32_t)(v.w == value) << 3);
   }
-  return 0xFFFFFFFFu;
+};
+template <> struct Vec<uint16_t> {
+  static constexpr uint32_t EPV = 8;
+  static __device__ __forceinline__ uint4 shift1(uint4 v, uint32_t nx) {
+    return make_uint4(__funnelshift_r(v.x, v.y, 16), __funnelshift_r(v.y, v.z, 16), __funnelshift_r(v.z, v.w, 16),
+                      __funnelshift_r(v.w, nx, 16));
+  }
+  static __device__ __forceinline__ uint32_t match(uint4 v, uint32_t value) {
+    uint32_t m = 0;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      m |= (uint32_t)((w[i] & 0xFFFFu) == value) << (2 * i);
+      m |= (uint32_t)((w[i] >> 16) == value) << (2 * i + 1);
+    }
+    return m;
+  }
+};
+
+// index of `value` in list[0..len) (unique), kNone when absent
+template <typename T>
+__device__ __noinline__ uint32_t list_find(const T* list, uint32_t len, uint32_t value, int lane) {
+  constexpr uint32_t EPV = Vec<T>::EPV;
+  constexpr int U = 4;
+  const uint4* lv = reinterpret_cast<const uint4*>(list);
+  const uint32_t ngroups = (len + EPV - 1) / EPV;
+  for (uint32_t gb = 0; gb < ngroups; gb += 32 * U) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t g = gb + u * 32 + lane;
+      v[u] = make_uint4(kNone, kNone, kNone, kNone);
+      if (g < ngroups) v[u] = lv[g];
+    }
+    uint32_t hit = kNone;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t g = gb + u * 32 + lane;
+      uint32_t m = Vec<T>::match(v[u], value);
+      if (g < ngroups && m) {
+        // the lowest matching element; a stale equal value beyond len can only sit above it
+        uint32_t e = g * EPV + (uint32_t)__ffs(m) - 1u;
+        if (e < len) hit = e;
+      }
+    }
+    uint32_t bal = __ballot_sync(FULL, hit != kNone);
+    if (bal) return __shfl_sync(FULL, hit, __ffs(bal) - 1);
+  }
+  return kNone;
 }
 
-// remove list[idx], keep order
-__device__ __forceinline__ void list_remove_at(uint32_t* list, uint32_t len, uint32_t idx, int lane) {
-  for (uint32_t base = idx; base + 1 < len; base += 32) {
-    uint32_t i = base + lane;
-    uint32_t v = 0;
-    if (i + 1 < len) v = list[i + 1];
+// remove list[idx], keep order.  May read up to 16 bytes past list[len) (allocation slack).
+template <typename T>
+__device__ __noinline__ void list_remove_at(T* list, uint32_t len, uint32_t idx, int lane) {
+  constexpr uint32_t EPV = Vec<T>::EPV;
+  constexpr int U = 4;
+  if (idx + 1 >= len) return;
+  const uint32_t last_dst = len - 2;
+  const uint32_t g0 = idx / EPV, g1 = last_dst / EPV;
+  {  // head: destination elements of group g0 (at most EPV-1 of them)
+    uint32_t head_end = (g0 + 1) * EPV < len - 1 ? (g0 + 1) * EPV : len - 1;
+    uint32_t e = idx + (uint32_t)lane;
+    T v = 0;
+    bool act = e < head_end;
+    if (act) v = list[e + 1];
     __syncwarp();
-    if (i + 1 < len) list[i] = v;
+    if (act) list[e] = v;
+    __syncwarp();
+  }
+  uint4* lv = reinterpret_cast<uint4*>(list);
+  for (uint32_t gb = g0 + 1; gb <= g1; gb += 32 * U) {
+    uint4 v[U];
+    uint32_t nx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t g = gb + u * 32 + lane;
+      if (g <= g1) {
+        v[u] = lv[g];
+        nx[u] = (uint32_t)list[(g + 1) * EPV];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t g = gb + u * 32 + lane;
+      if (g <= g1) lv[g] = Vec<T>::shift1(v[u], nx[u]);
+    }
     __syncwarp();
   }
 }
 
+__device__ __forceinline__ uint32_t round_cap(uint32_t c) { return (c + 7u) & ~7u; }
 __device__ __forceinline__ uint32_t gc_cap(uint32_t len) {
-  return len * 2 > (uint32_t)kMinListCap ? len * 2 : (uint32_t)kMinListCap;
+  return len * 2 > (uint32_t)kMinListCap ? round_cap(len * 2) : (uint32_t)kMinListCap;
 }
 
 // Arena compaction, in place, order inside every list untouched.  Pass 1 squeezes the blocks
-// down in ascending-offset order (cap = len); pass 2 spreads them out again from the last block
-// to the first so that block i gets cap = max(min, 2*len).  Visited blocks are tagged in the top
-// bit of cap.  O(S^2/32) bookkeeping — only runs when clone turnover has fragmented the arena.
-__device__ void arena_gc(Ctx& X, Rep& r) {
+// down in ascending-offset order (cap = len rounded to 16 bytes); pass 2 spreads them out again
+// from the last block to the first so that block i gets cap = max(min, 2*len).  Visited blocks
+// are tagged in the top bit of cap.  O(S^2/32) bookkeeping — only runs when clone turnover has
+// fragmented the arena.
+template <typename T>
+__device__ __noinline__ void arena_gc(Ctx<T>& X, Rep& r) {
   const int lane = X.lane;
   uint32_t top = 0;
   for (uint32_t step = 0; step < r.S; ++step) {
-    uint32_t best = 0xFFFFFFFFu, besti = 0xFFFFFFFFu;
+    uint32_t best = kNone, besti = kNone;
     for (uint32_t i = lane; i < r.S; i += 32) {
       uint32_t o = X.c_off[i];
       if (!(X.c_cap[i] & 0x80000000u) && o < best) { best = o; besti = i; }
@@ -279,7 +378,7 @@ __device__ void arena_gc(Ctx& X, Rep& r) {
     if (top != src) {
       for (uint32_t b = 0; b < l; b += 32) {  // dst < src: ascending chunks are safe
         uint32_t k = b + lane;
-        uint32_t v = 0;
+        T v = 0;
         if (k < l) v = X.arena[src + k];
         __syncwarp();
         if (k < l) X.arena[top + k] = v;
@@ -288,15 +387,15 @@ __device__ void arena_gc(Ctx& X, Rep& r) {
     }
     if (lane == 0) {
       X.c_off[i] = top;
-      X.c_cap[i] = l | 0x80000000u;
+      X.c_cap[i] = round_cap(l) | 0x80000000u;
     }
     __syncwarp();
-    top += l;
+    top += round_cap(l);
   }
   uint32_t total = 0;
   for (uint32_t i = lane; i < r.S; i += 32) total += gc_cap(X.c_len[i]);
   for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
-  if (total > X.A->arena_cap) {  // cannot happen when arena_cap >= 2*nv + kMinListCap*kTab
+  if (total > X.A->arena_cap) {  // cannot happen when arena_cap >= 2*nv + (kMinListCap + 8)*kTab
     for (uint32_t i = lane; i < r.S; i += 32) X.c_cap[i] &= 0x7FFFFFFFu;
     __syncwarp();
     r.arena_top = top;
@@ -305,18 +404,16 @@ __device__ void arena_gc(Ctx& X, Rep& r) {
   }
   for (uint32_t step = 0; step < r.S; ++step) {
     // still-tagged block with the largest (squeezed offset, index)
-    uint32_t best = 0, besti = 0xFFFFFFFFu;
+    uint32_t best = 0, besti = kNone;
     for (uint32_t i = lane; i < r.S; i += 32) {
       uint32_t o = X.c_off[i];
-      if ((X.c_cap[i] & 0x80000000u) && (besti == 0xFFFFFFFFu || o > best || (o == best && i > besti))) {
+      if ((X.c_cap[i] & 0x80000000u) && (besti == kNone || o > best || (o == best && i > besti))) {
         best = o; besti = i;
       }
     }
     for (int d = 16; d > 0; d >>= 1) {
       uint32_t ob = __shfl_xor_sync(FULL, best, d), oi = __shfl_xor_sync(FULL, besti, d);
-      if (oi != 0xFFFFFFFFu && (besti == 0xFFFFFFFFu || ob > best || (ob == best && oi > besti))) {
-        best = ob; besti = oi;
-      }
+      if (oi != kNone && (besti == kNone || ob > best || (ob == best && oi > besti))) { best = ob; besti = oi; }
     }
     const uint32_t i = besti, l = X.c_len[i], src = best;
     // new offset = total new capacity of the blocks not visited yet (all lie below src)
@@ -327,7 +424,7 @@ __device__ void arena_gc(Ctx& X, Rep& r) {
     if (noff != src && l > 0) {
       for (uint32_t cb = (l + 31) / 32; cb-- > 0;) {  // dst > src: descending chunks are safe
         uint32_t k = cb * 32 + lane;
-        uint32_t v = 0;
+        T v = 0;
         if (k < l) v = X.arena[src + k];
         __syncwarp();
         if (k < l) X.arena[noff + k] = v;
@@ -343,10 +440,10 @@ __device__ void arena_gc(Ctx& X, Rep& r) {
   r.arena_top = total;
 }
 
-// make room for one more element in list c (0-based clone index); returns false on failure
-__device__ bool list_reserve(Ctx& X, Rep& r, uint32_t c) {
+// slow path of list_append: list c is full
+template <typename T>
+__device__ __noinline__ bool list_grow(Ctx<T>& X, Rep& r, uint32_t c) {
   uint32_t len = X.c_len[c], cap = X.c_cap[c];
-  if (len < cap) return true;
   uint32_t ncap = cap * 2;
   if (r.arena_top + ncap > X.A->arena_cap) {
     arena_gc(X, r);
@@ -357,7 +454,6 @@ __device__ bool list_reserve(Ctx& X, Rep& r, uint32_t c) {
     ncap = cap * 2;
     if (r.arena_top + ncap > X.A->arena_cap) { r.status = JSB_ST_INTERNAL; return false; }
   }
-  // relocate to the top of the arena with doubled capacity
   const uint32_t src = X.c_off[c], dst = r.arena_top;
   for (uint32_t b = 0; b < len; b += 32) {
     uint32_t k = b + X.lane;
@@ -373,11 +469,14 @@ __device__ bool list_reserve(Ctx& X, Rep& r, uint32_t c) {
   return true;
 }
 
-__device__ __forceinline__ bool list_append(Ctx& X, Rep& r, uint32_t c, uint32_t site) {
-  if (!list_reserve(X, r, c)) return false;
+template <typename T>
+__device__ __forceinline__ bool list_append(Ctx<T>& X, Rep& r, uint32_t c, uint32_t site) {
+  if (X.c_len[c] >= X.c_cap[c]) {
+    if (!list_grow(X, r, c)) return false;
+  }
   if (X.lane == 0) {
     uint32_t len = X.c_len[c];
-    X.arena[X.c_off[c] + len] = site;
+    X.arena[X.c_off[c] + len] = (T)site;
     X.c_len[c] = len + 1;
   }
   __syncwarp();
@@ -385,18 +484,21 @@ __device__ __forceinline__ bool list_append(Ctx& X, Rep& r, uint32_t c, uint32_t
 }
 
 // filter!(e -> e != site, ca_subpop[c])
-__device__ __forceinline__ void list_remove_value(Ctx& X, uint32_t c, uint32_t site) {
+template <typename T>
+__device__ __forceinline__ void list_remove_value(Ctx<T>& X, uint32_t c, uint32_t site) {
   uint32_t len = X.c_len[c];
-  uint32_t* list = X.arena + X.c_off[c];
-  uint32_t idx = list_find(list, len, site, X.lane);
-  if (idx != 0xFFFFFFFFu) {
-    list_remove_at(list, len, idx, X.lane);
+  T* list = X.arena + X.c_off[c];
+  uint32_t idx = list_find<T>(list, len, site, X.lane);
+  if (idx != kNone) {
+    list_remove_at<T>(list, len, idx, X.lane);
     if (X.lane == 0) X.c_len[c] = len - 1;
     __syncwarp();
   }
 }
 
-__device__ bool new_clone(Ctx& X, Rep& r, uint32_t parent1, uint32_t label, double alpha, uint32_t first_site) {
+template <typename T>
+__device__ __noinline__ bool new_clone(Ctx<T>& X, Rep& r, uint32_t parent1, uint32_t label, double alpha,
+                                       uint32_t first_site) {
   const uint32_t c = r.S;
   if (r.arena_top + kMinListCap > X.A->arena_cap) {
     arena_gc(X, r);
@@ -410,21 +512,73 @@ __device__ bool new_clone(Ctx& X, Rep& r, uint32_t parent1, uint32_t label, doub
     X.c_alpha[c] = alpha;
     X.c_parent[c] = (uint16_t)parent1;
     X.c_label[c] = (uint16_t)label;
-    X.arena[r.arena_top] = first_site;
+    X.arena[r.arena_top] = (T)first_site;
   }
   __syncwarp();
   r.arena_top += kMinListCap;
   r.S = c + 1;
+  mark_dirty(r, c);
   return true;
 }
 
 // ---------------------------------------------------------------------------------------------
-// Class table: λ, θ and prob_cum of src/J_Space.jl:690-718, in the reference's summation order
+// Class boundaries: B_i = fl(B_{i-1} + α_i·n_i) (the reference's sequential `sum`, :692-695),
+// B_S = fl(birth + death), B_{S+1} = λ (:696-698).  Re-folded from the first changed clone.
 // ---------------------------------------------------------------------------------------------
-__device__ double acc_pairwise(double* __restrict__ v, double* __restrict__ c, double s, int i1, int n,
-                               double& mx, int lane) {
-  // Base._accumulate_pairwise! (Julia 1.7.3): blocks of < 128 are sequential; c holds the
-  // running maximum of prob_cum so that lower_bound == findfirst(k .<= prob_cum)
+template <typename T>
+__device__ __noinline__ void refold(Ctx<T>& X, Rep& r) {
+  const uint32_t S = r.S;
+  const uint32_t from = r.dirty_from < S ? r.dirty_from : S;
+  const int lane = X.lane;
+  double* B = (S + 2 <= (uint32_t)kSmemTable) ? X.s_B : X.g_B;
+  if (B != X.B) {  // the table outgrew the shared slice: carry the valid prefix over
+    for (uint32_t i = lane; i < from; i += 32) B[i] = X.B[i];
+    __syncwarp();
+    X.B = B;
+  }
+  double acc = from ? B[from - 1] : 0.0;  // 0.0 + w_0 == w_0 exactly
+  for (uint32_t base = from; base < S; base += 32) {
+    uint32_t i = base + lane;
+    double w = 0.0;
+    if (i < S) w = X.c_alpha[i] * (double)X.c_len[i];  // :693
+    X.s_w[lane] = w;
+    __syncwarp();
+    const uint32_t cnt = S - base < 32u ? S - base : 32u;
+    if (cnt == 32u) {
+#pragma unroll
+      for (uint32_t l = 0; l < 32u; ++l) {
+        acc = acc + X.s_w[l];
+        if (lane == 0) B[base + l] = acc;
+      }
+    } else {
+      for (uint32_t l = 0; l < cnt; ++l) {
+        acc = acc + X.s_w[l];
+        if (lane == 0) B[base + l] = acc;
+      }
+    }
+    __syncwarp();
+  }
+  const double death = X.P->rate_death * (double)r.n;     // :696
+  const double M = X.P->rate_migration * (double)r.n;     // :697
+  const double bd = acc + death;
+  const double lambda = bd + M;                           // :698
+  if (lane == 0) {
+    B[S] = bd;
+    B[S + 1] = lambda;
+  }
+  r.lambda = lambda;
+  r.theta = 1.0 / lambda;                                 // Exponential(1 / λ) :699
+  r.guard = ((X.P->quirks & JSB_QUIRK_DEBUG_WIDE_GUARD) ? 1e-3 : kGuardEps) * lambda;
+  r.exact_valid = false;
+  r.dirty_from = kNone;
+  __syncwarp();
+}
+
+// Exact prob_cum = cumsum(vcat(α_subpop ./ λ, death/λ, M/λ)) (:703-718) in Julia's
+// accumulate_pairwise! order, stored as its running maximum so that a lower bound equals
+// findfirst(k .<= prob_cum).  Only built when some k falls inside the guard band.
+__device__ double acc_pairwise(double* __restrict__ v, double* __restrict__ c, double s, int i1, int n, double& mx,
+                               int lane) {
   if (n < 128) {
     double s_ = v[i1];
     double cv = s + s_;
@@ -444,33 +598,24 @@ __device__ double acc_pairwise(double* __restrict__ v, double* __restrict__ c, d
   return sl + sr;
 }
 
-__device__ void rebuild_classes(Ctx& X, Rep& r) {
+template <typename T>
+__device__ __noinline__ void build_exact_table(Ctx<T>& X, Rep& r) {
   const int S = (int)r.S;
-  const int ncls = S + 2;
-  if (ncls <= kSmemClasses) { X.w = X.s_w; X.c = X.s_c; } else { X.w = X.g_w; X.c = X.g_c; }
-  double* __restrict__ w = X.w;
-  double* __restrict__ c = X.c;
-  for (int i = X.lane; i < S; i += 32) w[i] = X.c_alpha[i] * (double)X.c_len[i];  // :692-694
-  __syncwarp();
-  double birth = w[0];  // sum(α_subpop): sequential left fold
-  for (int i = 1; i < S; ++i) birth = birth + w[i];
-  double death = X.P->rate_death * (double)r.n;        // :696
-  double M = X.P->rate_migration * (double)r.n;        // :697
-  double lambda = birth + death + M;                   // :698
-  r.theta = 1.0 / lambda;                              // Exponential(1 / λ) :699
-  __syncwarp();
-  for (int i = X.lane; i < S; i += 32) w[i] = w[i] / lambda;  // Aₙ :703
+  double* __restrict__ w = X.g_w;
+  double* __restrict__ c = X.g_c;
+  const double lambda = r.lambda;
+  for (int i = X.lane; i < S; i += 32) w[i] = (X.c_alpha[i] * (double)X.c_len[i]) / lambda;  // Aₙ :703
   if (X.lane == 0) {
-    w[S] = death / lambda;   // Bₙ :704
-    w[S + 1] = M / lambda;   // Mₙ :705
+    w[S] = (X.P->rate_death * (double)r.n) / lambda;          // Bₙ :704
+    w[S + 1] = (X.P->rate_migration * (double)r.n) / lambda;  // Mₙ :705
   }
   __syncwarp();
-  // prob_cum = cumsum(prob_vet) :718
   double v1 = w[0];
   if (X.lane == 0) c[0] = v1;
   double mx = v1;
-  acc_pairwise(w, c, v1, 1, ncls - 1, mx, X.lane);
+  acc_pairwise(w, c, v1, 1, S + 1, mx, X.lane);
   __syncwarp();
+  r.exact_valid = true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -485,28 +630,30 @@ struct Eval {
   bool effective;
 };
 
-__device__ __forceinline__ Eval evaluate(const Ctx& X, const Rep& r, uint64_t q, uint64_t w_class, uint64_t w_cell,
-                                         uint64_t w_nbr) {
-  Eval e;
-  e.x = 0; e.cell = 0; e.pos = 0; e.occ = 0; e.effective = false;
-  const uint32_t S = r.S;
-  const double k = u01_53(w_class);  // :721
-  // findfirst(k .<= prob_cum) :722-723 as a lower bound on the running maximum
-  const double* c = X.c;
-  uint32_t lo = 0, len = S + 2;
+// first i in [0, n) with !(tab[i] < key); n when none
+__device__ __forceinline__ uint32_t lower_bound(const double* tab, uint32_t n, double key) {
+  uint32_t lo = 0, len = n;
   while (len > 0) {
     uint32_t half = len >> 1;
-    if (c[lo + half] < k) { lo += half + 1; len -= half + 1; } else { len = half; }
+    if (tab[lo + half] < key) { lo += half + 1; len -= half + 1; } else { len = half; }
   }
-  e.cls = lo;
-  if (lo >= S + 2) return e;  // reference: findfirst -> nothing; contract: null iteration
-  const uint32_t* list;
+  return lo;
+}
+
+template <typename T>
+__device__ __forceinline__ Eval evaluate_class(const Ctx<T>& X, const Rep& r, uint64_t q, uint32_t cls, uint64_t w_cell,
+                                               uint64_t w_nbr) {
+  Eval e;
+  e.cls = cls; e.x = 0; e.cell = 0; e.pos = 0; e.occ = 0; e.effective = false;
+  const uint32_t S = r.S;
+  if (cls >= S + 2) return e;  // reference: findfirst -> nothing; contract: null iteration
+  const T* list;
   uint32_t llen;
-  if (lo < S) { list = X.arena + X.c_off[lo]; llen = X.c_len[lo]; } else { list = X.Alist; llen = r.n; }
-  if (llen == 0) return e;    // rand(1:0) throws in the reference; contract: null iteration
+  if (cls < S) { list = X.arena + X.c_off[cls]; llen = X.c_len[cls]; } else { list = X.Alist; llen = r.n; }
+  if (llen == 0) return e;     // rand(1:0) throws in the reference; contract: null iteration
   e.x = bounded(X.key, w_cell, llen, q, DS_CELL_NBR, 0, 0);  // :727 / :746 / :762
-  e.cell = list[e.x];
-  if (lo == S) { e.effective = true; return e; }  // death :744-759 needs no neighbour
+  e.cell = (uint32_t)list[e.x];
+  if (cls == S) { e.effective = true; return e; }  // death :744-759 needs no neighbour
   const DevGraph& g = X.A->g;
   uint32_t deg, mask = 0, row0 = 0;
   if (g.kind == 0) { mask = lattice_mask(g, e.cell); deg = (uint32_t)__popc(mask); }
@@ -515,12 +662,12 @@ __device__ __forceinline__ Eval evaluate(const Ctx& X, const Rep& r, uint64_t q,
   uint32_t j = bounded(X.key, w_nbr, deg, q, DS_CELL_NBR, 0, 1);  // :730 / :764
   e.pos = (g.kind == 0) ? lattice_pick(g, e.cell, mask, j) : g.colidx[row0 + j];
   e.occ = X.clone[e.pos];
-  if (lo == S + 1) { e.effective = (e.occ == 0); return e; }  // migration :732
+  if (cls == S + 1) { e.effective = (e.occ == 0); return e; }  // migration :732
   bool rule = true;  // :767-786
   const int model = X.P->rule;
   if (model == JSB_RULE_CONTACT) rule = (e.occ == 0);
-  else if (model == JSB_RULE_VOTER) rule = !(e.occ != 0 && e.occ == lo + 1);
-  else if (model == JSB_RULE_HVOTER) rule = !(e.occ != 0 && X.c_alpha[lo] <= X.c_alpha[e.occ - 1]);
+  else if (model == JSB_RULE_VOTER) rule = !(e.occ != 0 && e.occ == cls + 1);
+  else if (model == JSB_RULE_HVOTER) rule = !(e.occ != 0 && X.c_alpha[cls] <= X.c_alpha[e.occ - 1]);
   e.effective = rule;
   return e;
 }
@@ -528,7 +675,8 @@ __device__ __forceinline__ Eval evaluate(const Ctx& X, const Rep& r, uint64_t q,
 // ---------------------------------------------------------------------------------------------
 // Event application (whole warp cooperates; control flow is warp-uniform)
 // ---------------------------------------------------------------------------------------------
-__device__ void apply_migration(Ctx& X, Rep& r, const Eval& e) {  // :733-741, migration_cell :592-613
+template <typename T>
+__device__ __noinline__ void apply_migration(Ctx<T>& X, Rep& r, const Eval& e) {  // :733-741, migration_cell :592-613
   uint32_t cid = X.cellid[e.cell];
   uint32_t cl = X.clone[e.cell];
   __syncwarp();
@@ -536,34 +684,36 @@ __device__ void apply_migration(Ctx& X, Rep& r, const Eval& e) {  // :733-741, m
     X.clone[e.cell] = 0;
     X.clone[e.pos] = (uint16_t)cl;
     X.cellid[e.pos] = cid;
-    X.Alist[r.n] = e.pos;  // push!(cs_alive, pos)
+    X.Alist[r.n] = (T)e.pos;  // push!(cs_alive, pos)
   }
   __syncwarp();
   log_row(X, r, JSB_EV_MIGRATION, JSB_EVF_GROUP_START, r.t, cid, 0, e.pos, e.cell + 1, cl, 0);
-  list_append(X, r, cl - 1, e.pos);                 // push!(ca_subpop[idx], pos)
-  list_remove_at(X.Alist, r.n + 1, e.x, X.lane);    // filter!(e -> e != cell, cs_alive)
-  list_remove_value(X, cl - 1, e.cell);             // filter!(e -> e != cell, ca_subpop[idx])
+  list_append(X, r, cl - 1, e.pos);                   // push!(ca_subpop[idx], pos)
+  list_remove_at<T>(X.Alist, r.n + 1, e.x, X.lane);   // filter!(e -> e != cell, cs_alive)
+  list_remove_value(X, cl - 1, e.cell);               // filter!(e -> e != cell, ca_subpop[idx])
   r.n_eff++;
   r.n_migr++;
 }
 
-__device__ void apply_death(Ctx& X, Rep& r, const Eval& e) {  // :746-759, cell_death :574-586
+template <typename T>
+__device__ __noinline__ void apply_death(Ctx<T>& X, Rep& r, const Eval& e) {  // :746-759, cell_death :574-586
   uint32_t cid = X.cellid[e.cell];
   uint32_t cl = X.clone[e.cell];
   __syncwarp();
   log_row(X, r, JSB_EV_DEATH, JSB_EVF_GROUP_START, r.t, cid, 0, e.cell, 0, cl, 0);
   if (X.lane == 0) X.clone[e.cell] = 0;
   __syncwarp();
-  list_remove_at(X.Alist, r.n, e.x, X.lane);
+  list_remove_at<T>(X.Alist, r.n, e.x, X.lane);
   list_remove_value(X, cl - 1, e.cell);
   r.n -= 1;
   r.n_eff++;
   r.n_deaths++;
+  mark_dirty(r, cl - 1);
 }
 
 // j-th (0-based) unused label of 1..1000; lane l owns labels 32l..32l+31
-__device__ __forceinline__ uint32_t pick_label(Rep& r, uint32_t j, int lane) {
-  uint32_t freew = ~r.used_w;
+__device__ __noinline__ uint32_t pick_label(uint32_t& used_w, uint32_t j, int lane) {
+  uint32_t freew = ~used_w;
   uint32_t cnt = (uint32_t)__popc(freew);
   uint32_t incl = cnt;
   for (int d = 1; d < 32; d <<= 1) {
@@ -579,17 +729,17 @@ __device__ __forceinline__ uint32_t pick_label(Rep& r, uint32_t j, int lane) {
     for (uint32_t q = 0; q < k; ++q) m &= m - 1;
     uint32_t bit = (uint32_t)__ffs(m) - 1u;
     lab = (uint32_t)lane * 32u + bit;
-    r.used_w |= 1u << bit;
+    used_w |= 1u << bit;
   }
   uint32_t who = __ballot_sync(FULL, mine);
   return __shfl_sync(FULL, lab, __ffs(who) - 1);
 }
 
 // randn by the polar method on contract draws (D9)
-__device__ double contract_randn(const Ctx& X, uint64_t iter) {
+__device__ __noinline__ double contract_randn(Key key, uint64_t iter) {
   for (uint32_t attempt = 0;; ++attempt) {
     uint64_t a, b;
-    draw_block(X.key, iter, 0, DS_NORMAL, attempt, a, b);
+    draw_block(key, iter, 0, DS_NORMAL, attempt, a, b);
     double v1 = 2.0 * u01_53(a) - 1.0;
     double v2 = 2.0 * u01_53(b) - 1.0;
     double s = v1 * v1 + v2 * v2;
@@ -598,9 +748,29 @@ __device__ double contract_randn(const Ctx& X, uint64_t iter) {
   }
 }
 
+// method 2: first child of the genotype's last driver, in edge-list order, whose genotype is not
+// in set_mut yet (:450-473); -1 when none
+template <typename T>
+__device__ __noinline__ int tree_child(const Ctx<T>& X, const Rep& r, uint32_t sp) {
+  const DevPoint& P = *X.P;
+  int child_node = -1;
+  int last = (int)X.c_label[sp - 1] - 1;
+  for (int ed = 0; ed < P.n_edges && child_node < 0; ++ed) {
+    if (X.edge_parent[ed] != last) continue;
+    int cand = X.edge_child[ed];
+    bool present = false;  // new_mut ∈ set_mut :466
+    for (uint32_t s0 = X.lane; s0 < r.S; s0 += 32)
+      if (X.c_parent[s0] == sp && (int)X.c_label[s0] - 1 == cand) present = true;
+    present = __any_sync(FULL, present);
+    if (!present) child_node = cand;
+  }
+  return child_node;
+}
+
 // cell_birth :320-416 / :419-537 plus the caller's bookkeeping :803-808.  Returns false when the
 // replicate must stop.
-__device__ bool apply_birth(Ctx& X, Rep& r, const Eval& e) {
+template <typename T>
+__device__ __noinline__ bool apply_birth(Ctx<T>& X, Rep& r, const Eval& e) {
   const DevPoint& P = *X.P;
   const uint32_t sp = e.cls + 1;  // :Subpop of the dividing cell (== min)
   uint64_t wa, wb;
@@ -609,19 +779,8 @@ __device__ bool apply_birth(Ctx& X, Rep& r, const Eval& e) {
   int child_node = -1;
   bool driver;
   if (P.method == JSB_METHOD_TREE) {
-    if (rr <= P.mu) {  // :448
-      int last = (int)X.c_label[sp - 1] - 1;
-      for (int ed = 0; ed < P.n_edges && child_node < 0; ++ed) {  // edge-list order :456
-        if (X.edge_parent[ed] != last) continue;
-        int cand = X.edge_child[ed];
-        bool present = false;  // new_mut ∈ set_mut :466
-        for (uint32_t s0 = X.lane; s0 < r.S; s0 += 32)
-          if (X.c_parent[s0] == sp && (int)X.c_label[s0] - 1 == cand) present = true;
-        present = __any_sync(FULL, present);
-        if (!present) child_node = cand;
-      }
-    }
-    driver = child_node >= 0;  // :476
+    if (rr <= P.mu) child_node = tree_child(X, r, sp);  // :448
+    driver = child_node >= 0;                            // :476
   } else {
     driver = !(rr > P.mu);  // :348
   }
@@ -634,6 +793,7 @@ __device__ bool apply_birth(Ctx& X, Rep& r, const Eval& e) {
     uint32_t pid = X.cellid[e.pos];
     __syncwarp();
     list_remove_value(X, e.occ - 1, e.pos);
+    mark_dirty(r, e.occ - 1);
     log_row(X, r, JSB_EV_DEATH, JSB_EVF_DISPLACED | first_flag, r.t, pid, 0, e.pos, 0, e.occ, 0);
     first_flag = 0;
     r.n_disp++;
@@ -652,6 +812,7 @@ __device__ bool apply_birth(Ctx& X, Rep& r, const Eval& e) {
     }
     __syncwarp();
     if (!list_append(X, r, sp - 1, e.pos)) return false;
+    mark_dirty(r, sp - 1);
   } else {
     uint32_t label;
     double nalpha;
@@ -659,12 +820,12 @@ __device__ bool apply_birth(Ctx& X, Rep& r, const Eval& e) {
       label = (uint32_t)child_node + 1;
       nalpha = X.node_rate[child_node];  // :503-505
     } else {
-      uint32_t n_free = 1000u - (r.S);  // one label per clone, founder uses label 1
+      uint32_t n_free = 1000u - r.S;  // one label per clone, the founder holds label 1
       uint64_t a, b;
       draw_block(X.key, r.it, 0, DS_LABEL, 0, a, b);
       uint32_t j = bounded(X.key, a, n_free, r.it, DS_LABEL, 0, 0);  // :371
-      label = pick_label(r, j, X.lane);
-      double z = contract_randn(X, r.it);  // :565-566
+      label = pick_label(r.used_w, j, X.lane);
+      double z = contract_randn(X.key, r.it);  // :565-566
       nalpha = X.c_alpha[sp - 1] + fabs(P.adv_mean + P.adv_std * z);
     }
     const uint32_t nsp = r.S + 1;
@@ -693,9 +854,10 @@ __device__ bool apply_birth(Ctx& X, Rep& r, const Eval& e) {
     }
   }
   if (e.occ == 0) {  // :803-806
-    if (X.lane == 0) X.Alist[r.n] = e.pos;
+    if (X.lane == 0) X.Alist[r.n] = (T)e.pos;
     __syncwarp();
     r.n += 1;
+    mark_dirty(r, r.S);  // death and migration weights changed (B_S, B_{S+1})
   }
   r.n_eff++;
   r.n_births++;
@@ -704,7 +866,8 @@ __device__ bool apply_birth(Ctx& X, Rep& r, const Eval& e) {
 
 // Excision block :813-838 / :1036-1061: StatsBase.sample(rng, cs_alive, k; replace=false), then
 // cell_death for each sampled vertex in sample order, logged at time tb.
-__device__ void apply_excision(Ctx& X, Rep& r, double tb, double ratio) {
+template <typename T>
+__device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double ratio) {
   const uint32_t n = r.n;
   const double taked = (double)n * ratio;  // :819
   long long kk = (long long)trunc(taked);
@@ -718,7 +881,7 @@ __device__ void apply_excision(Ctx& X, Rep& r, double tb, double ratio) {
     uint64_t a, b;
     draw_block(X.key, r.it, 0, DS_EXCISION, 0, a, b);
     uint32_t i = bounded(X.key, a, n, r.it, DS_EXCISION, 0, 0);
-    if (lane == 0) samp[0] = X.Alist[i];
+    if (lane == 0) samp[0] = (uint32_t)X.Alist[i];
   } else if (k == 2) {  // samplepair
     uint64_t a, b;
     draw_block(X.key, r.it, 0, DS_EXCISION, 0, a, b);
@@ -726,8 +889,8 @@ __device__ void apply_excision(Ctx& X, Rep& r, double tb, double ratio) {
     draw_block(X.key, r.it, 0, DS_EXCISION, 1, a, b);
     uint32_t i2 = bounded(X.key, a, n - 1, r.it, DS_EXCISION, 1, 0) + 1;
     if (lane == 0) {
-      samp[0] = X.Alist[i1 - 1];
-      samp[1] = X.Alist[(i2 == i1 ? n : i2) - 1];
+      samp[0] = (uint32_t)X.Alist[i1 - 1];
+      samp[1] = (uint32_t)X.Alist[(i2 == i1 ? n : i2) - 1];
     }
   } else if (k > 2 && (unsigned long long)n < (unsigned long long)k * 24ull) {  // fisher_yates_sample!
     for (uint32_t i = lane; i < n; i += 32) inds[i] = i;
@@ -748,7 +911,7 @@ __device__ void apply_excision(Ctx& X, Rep& r, double tb, double ratio) {
           uint32_t tj = inds[j], ti = inds[ii];
           inds[j] = ti;
           inds[ii] = tj;
-          samp[ii] = X.Alist[tj];
+          samp[ii] = (uint32_t)X.Alist[tj];
         }
       }
       __syncwarp();
@@ -768,7 +931,7 @@ __device__ void apply_excision(Ctx& X, Rep& r, double tb, double ratio) {
           if (!inds[idx]) break;
         }
         inds[idx] = 1;
-        samp[i] = X.Alist[idx];
+        samp[i] = (uint32_t)X.Alist[idx];
       }
     }
   }
@@ -808,7 +971,7 @@ __device__ void apply_excision(Ctx& X, Rep& r, double tb, double ratio) {
     uint32_t wpos = 0;
     for (uint32_t base = 0; base < n; base += 32) {
       uint32_t i = base + lane;
-      uint32_t v = 0;
+      T v = 0;
       bool keep = false;
       if (i < n) { v = X.Alist[i]; keep = X.clone[v] != 0; }
       uint32_t m = __ballot_sync(FULL, keep);
@@ -819,11 +982,11 @@ __device__ void apply_excision(Ctx& X, Rep& r, double tb, double ratio) {
   }
   for (uint32_t c = 0; c < r.S; ++c) {
     uint32_t len = X.c_len[c];
-    uint32_t* list = X.arena + X.c_off[c];
+    T* list = X.arena + X.c_off[c];
     uint32_t wpos = 0;
     for (uint32_t base = 0; base < len; base += 32) {
       uint32_t i = base + lane;
-      uint32_t v = 0;
+      T v = 0;
       bool keep = false;
       if (i < len) { v = list[i]; keep = X.clone[v] != 0; }
       uint32_t m = __ballot_sync(FULL, keep);
@@ -837,12 +1000,14 @@ __device__ void apply_excision(Ctx& X, Rep& r, double tb, double ratio) {
   r.n = n - k;
   r.n_exc += k;
   r.n_eff++;  // one series push :835-836
+  r.dirty_from = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Seeding: initialize_graph :79-163 and the initial lists :655-683
 // ---------------------------------------------------------------------------------------------
-__device__ void seed_replicate(Ctx& X, Rep& r) {
+template <typename T>
+__device__ __noinline__ void seed_replicate(Ctx<T>& X, Rep& r) {
   const DevPoint& P = *X.P;
   const DevGraph& g = X.A->g;
   const int lane = X.lane;
@@ -861,7 +1026,7 @@ __device__ void seed_replicate(Ctx& X, Rep& r) {
       if (lane == 0) {
         X.clone[v0] = 1;
         X.cellid[v0] = 1;
-        X.Alist[0] = v0;
+        X.Alist[0] = (T)v0;
       }
       n0 = 1;
     }
@@ -883,7 +1048,7 @@ __device__ void seed_replicate(Ctx& X, Rep& r) {
         X.clone[pos] = 1;
         X.cellid[pos] = (uint32_t)i + 1;
       }
-      for (uint32_t q = 0; q < cnt; ++q) X.Alist[q] = X.samp[q];
+      for (uint32_t q = 0; q < cnt; ++q) X.Alist[q] = (T)X.samp[q];
     }
     n0 = (uint32_t)P.n_start;
   }
@@ -913,160 +1078,11 @@ __device__ void seed_replicate(Ctx& X, Rep& r) {
   __syncwarp();
 }
 
-// ---------------------------------------------------------------------------------------------
-// One replicate
-// ---------------------------------------------------------------------------------------------
-__device__ void run_replicate(Ctx& X) {
+template <typename T>
+__device__ __noinline__ void write_outputs(Ctx<T>& X, Rep& r) {
   const RunArgs& A = *X.A;
-  const DevPoint& P = *X.P;
   const int lane = X.lane;
-  Rep r;
-  r.t = 0.0; r.theta = 0.0; r.it = 0; r.nlog = 0; r.cur_chunk = 0;
-  r.bott_id = P.n_bott > 0 ? 1 : 0;  // :668-672
-  r.snap_idx = 0;
-  r.status = JSB_ST_OK;
-  r.n_eff = r.n_births = r.n_deaths = r.n_migr = r.n_disp = r.n_exc = 0;
-  r.log_on = (A.flags & JSB_OUT_EVENTS) != 0;
-  seed_replicate(X, r);
-
-  const bool intent = (P.quirks & JSB_QUIRK_EXCISION_INTENT) != 0;
-  const uint32_t width = (P.quirks & JSB_QUIRK_DEBUG_SERIAL) ? 1u : 32u;
-  const uint32_t wmask = width == 32 ? FULL : ((1u << width) - 1u);
   const uint32_t nv = A.g.nv;
-  bool dirty = true;
-
-  for (;;) {
-    if (!(r.t < P.Tf && r.n > 0)) {  // loop test :687-688
-      if (P.rate_death == 0.0 && r.n == nv) r.status = JSB_ST_NONTERMINATING;
-      break;
-    }
-    if (dirty) { rebuild_classes(X, r); dirty = false; }
-
-    // ---- 32 iterations' worth of draws -------------------------------------------------------
-    const uint64_t q = r.it + 1 + (uint64_t)lane;
-    uint64_t wa, wb, wc, wd;
-    draw_block(X.key, q, 0, DS_TIME_CLASS, 0, wa, wb);
-    draw_block(X.key, q, 0, DS_CELL_NBR, 0, wc, wd);
-    const double dt = (-contract_log(u01_open(wa))) * r.theta;  // :699
-    Eval e = evaluate(X, r, q, wb, wc, wd);
-    const uint32_t effmask = __ballot_sync(FULL, e.effective) & wmask;
-    const uint32_t jE = effmask ? (uint32_t)__ffs(effmask) - 1u : width - 1u;
-
-    // ---- time chain over the lanes that may commit --------------------------------------------
-    double tend = r.t;
-    for (uint32_t l = 0; l <= jE; ++l) tend = tend + __shfl_sync(FULL, dt, (int)l);  // :701
-
-    // ---- can anything other than the event at jE happen in (t, tend]? --------------------------
-    bool slow = !(tend < P.Tf);
-    if (P.max_iter && r.it + jE + 1 > P.max_iter) slow = true;
-    if (r.snap_idx < P.n_snap && tend > X.tsnap[r.snap_idx]) slow = true;
-    if (P.n_bott > 0) {
-      if (intent) {
-        if (r.bott_id > 0) { double tb = X.tb[r.bott_id - 1]; if (tb > r.t && tb <= tend) slow = true; }
-      } else if (P.method == JSB_METHOD_TREE) {
-        if (r.it + 1 < (uint64_t)P.n_bott) slow = true;
-        else { double tb = X.tb[P.n_bott - 1]; if (tb > r.t && tb <= tend) slow = true; }
-      } else {
-        double tb = X.tb[0]; if (tb > r.t && tb <= tend) slow = true;
-      }
-    }
-
-    uint32_t j = jE;
-    bool do_event = effmask != 0;
-    bool do_snap = false, do_bott = false;
-    double tb_fire = 0.0, ratio_fire = 0.0;
-    double t_old = r.t;
-
-    if (!slow) {
-      r.it += jE + 1;
-      r.t = tend;
-    } else {
-      // per-lane (t_old, t_curr) of every candidate iteration
-      double my_prev = r.t, my_t = r.t, run = r.t;
-      for (uint32_t l = 0; l <= jE; ++l) {
-        double prev = run;
-        run = run + __shfl_sync(FULL, dt, (int)l);
-        if ((uint32_t)lane == l) { my_prev = prev; my_t = run; }
-      }
-      const bool in_range = (uint32_t)lane <= jE;
-      const bool stop_l = in_range && !(my_prev < P.Tf);
-      const bool maxit_l = in_range && P.max_iter && (r.it + (uint64_t)lane >= P.max_iter);
-      bool bott_l = false;
-      double tb_l = 0.0, ratio_l = 0.0;
-      if (in_range && P.n_bott > 0) {
-        int id = 0;
-        if (intent) id = r.bott_id;
-        else if (P.method == JSB_METHOD_TREE) id = (int)(q < (uint64_t)P.n_bott ? q : (uint64_t)P.n_bott);  // :1062-1064
-        else id = 1;  // method 1 never advances id_bottleneck
-        if (id > 0) {
-          tb_l = X.tb[id - 1];
-          ratio_l = X.ratio[id - 1];
-          bott_l = tb_l > my_prev && tb_l <= my_t;  // :814-815
-        }
-      }
-      const bool snap_l = in_range && r.snap_idx < P.n_snap && my_t > X.tsnap[r.snap_idx];  // :708-710
-      const bool special = stop_l || maxit_l || bott_l || snap_l || (in_range && e.effective);
-      const uint32_t smask = __ballot_sync(FULL, special) & wmask;
-      if (smask == 0) {  // cannot happen when slow was triggered by tend >= Tf etc. but be safe
-        r.it += jE + 1;
-        r.t = tend;
-        continue;
-      }
-      j = (uint32_t)__ffs(smask) - 1u;
-      const bool stop_j = __shfl_sync(FULL, (int)stop_l, (int)j) != 0;
-      const bool maxit_j = __shfl_sync(FULL, (int)maxit_l, (int)j) != 0;
-      const double prev_j = __shfl_sync(FULL, my_prev, (int)j);
-      const double t_j = __shfl_sync(FULL, my_t, (int)j);
-      if (stop_j || maxit_j) {
-        r.it += j;
-        r.t = prev_j;
-        if (stop_j) { if (P.rate_death == 0.0 && r.n == nv) r.status = JSB_ST_NONTERMINATING; }
-        else r.status = JSB_ST_MAX_ITER;
-        break;
-      }
-      r.it += j + 1;
-      t_old = prev_j;
-      r.t = t_j;
-      do_event = __shfl_sync(FULL, (int)e.effective, (int)j) != 0;
-      do_snap = __shfl_sync(FULL, (int)snap_l, (int)j) != 0;
-      do_bott = __shfl_sync(FULL, (int)bott_l, (int)j) != 0;
-      tb_fire = __shfl_sync(FULL, tb_l, (int)j);
-      ratio_fire = __shfl_sync(FULL, ratio_l, (int)j);
-    }
-    (void)t_old;
-
-    if (do_snap) {  // :708-714
-      if (lane == 0 && A.snaps) {
-        jsb_snapshot s;
-        s.time = r.t; s.iteration = r.it; s.n_events_before = r.nlog; s.n_alive = r.n;
-        s.index = (uint32_t)r.snap_idx;
-        A.snaps[(size_t)X.local_idx * A.max_snap + r.snap_idx] = s;
-      }
-      r.snap_idx++;
-    }
-    bool keep_going = true;
-    if (do_event) {
-      Eval ej;
-      ej.cls = __shfl_sync(FULL, e.cls, (int)j);
-      ej.x = __shfl_sync(FULL, e.x, (int)j);
-      ej.cell = __shfl_sync(FULL, e.cell, (int)j);
-      ej.pos = __shfl_sync(FULL, e.pos, (int)j);
-      ej.occ = __shfl_sync(FULL, e.occ, (int)j);
-      ej.effective = true;
-      if (ej.cls == r.S + 1) apply_migration(X, r, ej);
-      else if (ej.cls == r.S) { apply_death(X, r, ej); dirty = true; }
-      else { keep_going = apply_birth(X, r, ej); dirty = true; }
-    }
-    if (!keep_going) break;
-    if (do_bott) {
-      apply_excision(X, r, tb_fire, ratio_fire);
-      dirty = true;
-      if (intent) r.bott_id = (r.bott_id < P.n_bott) ? r.bott_id + 1 : 0;
-    }
-    if (r.status == JSB_ST_INTERNAL) break;
-  }
-
-  // ---- outputs --------------------------------------------------------------------------------
   __syncwarp();
   if (lane == 0) {
     jsb_summary s;
@@ -1085,7 +1101,6 @@ __device__ void run_replicate(Ctx& X) {
     s.status = r.status;
     A.summaries[X.local_idx] = s;
   }
-  // clone table
   long long off = -1;
   if (A.clone_pool) {
     unsigned long long o = 0;
@@ -1116,32 +1131,228 @@ __device__ void run_replicate(Ctx& X) {
   if (A.out_lists) {
     uint32_t* la = A.out_lists + (size_t)X.local_idx * 2 * nv;
     uint32_t* ll = la + nv;
-    for (uint32_t i = lane; i < r.n; i += 32) la[i] = X.Alist[i] + 1;
+    for (uint32_t i = lane; i < r.n; i += 32) la[i] = (uint32_t)X.Alist[i] + 1;
     uint32_t wpos = 0;
     for (uint32_t c = 0; c < r.S; ++c) {
       uint32_t len = X.c_len[c];
-      const uint32_t* list = X.arena + X.c_off[c];
-      for (uint32_t i = lane; i < len; i += 32) ll[wpos + i] = list[i] + 1;
+      const T* list = X.arena + X.c_off[c];
+      for (uint32_t i = lane; i < len; i += 32) ll[wpos + i] = (uint32_t)list[i] + 1;
       wpos += len;
     }
   }
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) ssa_kernel(const __grid_constant__ RunArgs A) {
-  __shared__ double s_tab[kWarpsPerBlock][2][kSmemClasses];
+// Per-lane (t_old, t_curr) of the candidate iterations and everything that can happen besides
+// the first state-changing event: loop exit at Tf, max_iterations, excision, snapshot.  Only
+// reached when the batch's time span touches one of those (a handful of times per replicate).
+struct SlowOut {
+  uint32_t j;
+  bool stop, maxit, do_event, do_snap, do_bott;
+  double t_prev, t_cur, tb, ratio;
+};
+
+template <typename T>
+__device__ __noinline__ SlowOut slow_scan(const Ctx<T>& X, const Rep& r, double dt, bool effective, uint32_t jE,
+                                          uint32_t wmask, uint64_t q) {
+  const DevPoint& P = *X.P;
+  const int lane = X.lane;
+  const bool intent = (P.quirks & JSB_QUIRK_EXCISION_INTENT) != 0;
+  double my_prev = r.t, my_t = r.t, run = r.t;
+  for (uint32_t l = 0; l <= jE; ++l) {
+    double prev = run;
+    run = run + __shfl_sync(FULL, dt, (int)l);  // :701
+    if ((uint32_t)lane == l) { my_prev = prev; my_t = run; }
+  }
+  const bool in_range = (uint32_t)lane <= jE;
+  const bool stop_l = in_range && !(my_prev < P.Tf);  // loop test :687 (n > 0 holds inside a batch)
+  const bool maxit_l = in_range && P.max_iter && (r.it + (uint64_t)lane >= P.max_iter);
+  bool bott_l = false;
+  double tb_l = 0.0, ratio_l = 0.0;
+  if (in_range && P.n_bott > 0) {
+    int id;
+    if (intent) id = r.bott_id;
+    else if (P.method == JSB_METHOD_TREE) id = (int)(q < (uint64_t)P.n_bott ? q : (uint64_t)P.n_bott);  // :1062-1064
+    else id = 1;  // method 1 never advances id_bottleneck
+    if (id > 0) {
+      tb_l = X.tb[id - 1];
+      ratio_l = X.ratio[id - 1];
+      bott_l = tb_l > my_prev && tb_l <= my_t;  // :814-815
+    }
+  }
+  const bool snap_l = in_range && r.snap_idx < P.n_snap && my_t > X.tsnap[r.snap_idx];  // :708-710
+  const bool special = stop_l || maxit_l || bott_l || snap_l || (in_range && effective);
+  const uint32_t smask = __ballot_sync(FULL, special) & wmask;
+  SlowOut o;
+  if (smask == 0) {  // nothing special after all: commit the whole range
+    o.j = jE; o.stop = o.maxit = o.do_event = o.do_snap = o.do_bott = false;
+    o.t_prev = 0.0; o.t_cur = __shfl_sync(FULL, my_t, (int)jE); o.tb = o.ratio = 0.0;
+    return o;
+  }
+  const int j = __ffs(smask) - 1;
+  o.j = (uint32_t)j;
+  o.stop = __shfl_sync(FULL, (int)stop_l, j) != 0;
+  o.maxit = __shfl_sync(FULL, (int)maxit_l, j) != 0;
+  o.do_event = __shfl_sync(FULL, (int)effective, j) != 0;
+  o.do_snap = __shfl_sync(FULL, (int)snap_l, j) != 0;
+  o.do_bott = __shfl_sync(FULL, (int)bott_l, j) != 0;
+  o.t_prev = __shfl_sync(FULL, my_prev, j);
+  o.t_cur = __shfl_sync(FULL, my_t, j);
+  o.tb = __shfl_sync(FULL, tb_l, j);
+  o.ratio = __shfl_sync(FULL, ratio_l, j);
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One replicate
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ void run_replicate(Ctx<T>& X) {
+  const RunArgs& A = *X.A;
+  const DevPoint& P = *X.P;
+  const int lane = X.lane;
+  Rep r;
+  r.t = 0.0; r.theta = 0.0; r.lambda = 0.0; r.guard = 0.0; r.it = 0; r.nlog = 0; r.cur_chunk = 0;
+  r.bott_id = P.n_bott > 0 ? 1 : 0;  // :668-672
+  r.snap_idx = 0;
+  r.status = JSB_ST_OK;
+  r.n_eff = r.n_births = r.n_deaths = r.n_migr = r.n_disp = r.n_exc = 0;
+  r.log_on = (A.flags & JSB_OUT_EVENTS) != 0;
+  r.exact_valid = false;
+  r.dirty_from = 0;
+  X.B = X.s_B;
+  seed_replicate(X, r);
+
+  const bool intent = (P.quirks & JSB_QUIRK_EXCISION_INTENT) != 0;
+  const bool force_exact = (P.quirks & JSB_QUIRK_DEBUG_EXACT_CLASSES) != 0;
+  const uint32_t width = (P.quirks & JSB_QUIRK_DEBUG_SERIAL) ? 1u : 32u;
+  const uint32_t wmask = width == 32 ? FULL : ((1u << width) - 1u);
+  const uint32_t nv = A.g.nv;
+
+  for (;;) {
+    if (!(r.t < P.Tf && r.n > 0)) {  // loop test :687-688
+      if (P.rate_death == 0.0 && r.n == nv) r.status = JSB_ST_NONTERMINATING;
+      break;
+    }
+    if (r.dirty_from != kNone) refold(X, r);
+
+    // ---- 32 iterations' worth of draws -------------------------------------------------------
+    const uint64_t q = r.it + 1 + (uint64_t)lane;
+    uint64_t wa, wb, wc, wd;
+    draw_block(X.key, q, 0, DS_TIME_CLASS, 0, wa, wb);
+    draw_block(X.key, q, 0, DS_CELL_NBR, 0, wc, wd);
+    const double dt = (-contract_log(u01_open(wa))) * r.theta;  // :699
+
+    // ---- event class: k·λ against the folded boundaries, exact table inside the guard band ----
+    const double k = u01_53(wb);  // :721
+    uint32_t cls;
+    {
+      const double key = k * r.lambda;
+      const uint32_t nb = r.S + 2;
+      cls = lower_bound(X.B, nb, key);
+      bool unc = force_exact || cls >= nb || (X.B[cls] - key <= r.guard) || (cls > 0 && key - X.B[cls - 1] <= r.guard);
+      if (__ballot_sync(FULL, unc) & wmask) {
+        if (!r.exact_valid) build_exact_table(X, r);
+        if (unc) cls = lower_bound(X.g_c, nb, k);  // findfirst(k .<= prob_cum) :722-723
+      }
+    }
+    Eval e = evaluate_class(X, r, q, cls, wc, wd);
+    const uint32_t effmask = __ballot_sync(FULL, e.effective) & wmask;
+    const uint32_t jE = effmask ? (uint32_t)__ffs(effmask) - 1u : width - 1u;
+
+    // ---- time chain over the lanes that may commit --------------------------------------------
+    double tend = r.t;
+    for (uint32_t l = 0; l <= jE; ++l) tend = tend + __shfl_sync(FULL, dt, (int)l);  // :701
+
+    // ---- can anything other than the event at jE happen in (t, tend]? --------------------------
+    bool slow = !(tend < P.Tf);
+    if (P.max_iter && r.it + jE + 1 > P.max_iter) slow = true;
+    if (r.snap_idx < P.n_snap && tend > X.tsnap[r.snap_idx]) slow = true;
+    if (P.n_bott > 0) {
+      if (intent) {
+        if (r.bott_id > 0) { double tb = X.tb[r.bott_id - 1]; if (tb > r.t && tb <= tend) slow = true; }
+      } else if (P.method == JSB_METHOD_TREE) {
+        if (r.it + 1 < (uint64_t)P.n_bott) slow = true;
+        else { double tb = X.tb[P.n_bott - 1]; if (tb > r.t && tb <= tend) slow = true; }
+      } else {
+        double tb = X.tb[0]; if (tb > r.t && tb <= tend) slow = true;
+      }
+    }
+
+    uint32_t j = jE;
+    bool do_event = effmask != 0;
+    bool do_snap = false, do_bott = false;
+    double tb_fire = 0.0, ratio_fire = 0.0;
+
+    if (!slow) {
+      r.it += jE + 1;
+      r.t = tend;
+    } else {
+      SlowOut o = slow_scan(X, r, dt, e.effective, jE, wmask, q);
+      j = o.j;
+      if (o.stop || o.maxit) {
+        r.it += j;
+        r.t = o.t_prev;
+        if (o.stop) { if (P.rate_death == 0.0 && r.n == nv) r.status = JSB_ST_NONTERMINATING; }
+        else r.status = JSB_ST_MAX_ITER;
+        break;
+      }
+      r.it += j + 1;
+      r.t = o.t_cur;
+      do_event = o.do_event;
+      do_snap = o.do_snap;
+      do_bott = o.do_bott;
+      tb_fire = o.tb;
+      ratio_fire = o.ratio;
+    }
+
+    if (do_snap) {  // :708-714
+      if (lane == 0 && A.snaps) {
+        jsb_snapshot s;
+        s.time = r.t; s.iteration = r.it; s.n_events_before = r.nlog; s.n_alive = r.n;
+        s.index = (uint32_t)r.snap_idx;
+        A.snaps[(size_t)X.local_idx * A.max_snap + r.snap_idx] = s;
+      }
+      r.snap_idx++;
+    }
+    bool keep_going = true;
+    if (do_event) {
+      Eval ej;
+      ej.cls = __shfl_sync(FULL, e.cls, (int)j);
+      ej.x = __shfl_sync(FULL, e.x, (int)j);
+      ej.cell = __shfl_sync(FULL, e.cell, (int)j);
+      ej.pos = __shfl_sync(FULL, e.pos, (int)j);
+      ej.occ = __shfl_sync(FULL, e.occ, (int)j);
+      ej.effective = true;
+      if (ej.cls == r.S + 1) apply_migration(X, r, ej);
+      else if (ej.cls == r.S) apply_death(X, r, ej);
+      else keep_going = apply_birth(X, r, ej);
+    }
+    if (!keep_going) break;
+    if (do_bott) {
+      apply_excision(X, r, tb_fire, ratio_fire);
+      if (intent) r.bott_id = (r.bott_id < P.n_bott) ? r.bott_id + 1 : 0;
+    }
+    if (r.status == JSB_ST_INTERNAL) break;
+  }
+  write_outputs(X, r);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) ssa_kernel(const __grid_constant__ RunArgs A) {
+  __shared__ double s_tab[kWarpsPerBlock][kSmemTable + 32];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint64_t slot = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
-  const WsLayout L = ws_layout(A.g.nv, A.arena_cap);
+  const WsLayout L = ws_layout(A.g.nv, A.arena_cap, (uint32_t)sizeof(T));
   uint8_t* base = A.ws + slot * A.ws_stride;
-  Ctx X;
+  Ctx<T> X;
   X.A = &A;
   X.lane = lane;
   X.clone = reinterpret_cast<uint16_t*>(base + L.clone);
   X.cellid = reinterpret_cast<uint32_t*>(base + L.cellid);
-  X.Alist = reinterpret_cast<uint32_t*>(base + L.A);
-  X.arena = reinterpret_cast<uint32_t*>(base + L.arena);
+  X.Alist = reinterpret_cast<T*>(base + L.A);
+  X.arena = reinterpret_cast<T*>(base + L.arena);
   X.inds = reinterpret_cast<uint32_t*>(base + L.inds);
   X.samp = reinterpret_cast<uint32_t*>(base + L.samp);
   X.c_off = reinterpret_cast<uint32_t*>(base + L.c_off);
@@ -1150,12 +1361,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ssa_kernel(const __grid_c
   X.c_alpha = reinterpret_cast<double*>(base + L.c_alpha);
   X.c_parent = reinterpret_cast<uint16_t*>(base + L.c_parent);
   X.c_label = reinterpret_cast<uint16_t*>(base + L.c_label);
+  X.g_B = reinterpret_cast<double*>(base + L.g_B);
   X.g_w = reinterpret_cast<double*>(base + L.g_w);
   X.g_c = reinterpret_cast<double*>(base + L.g_c);
-  X.s_w = s_tab[warp][0];
-  X.s_c = s_tab[warp][1];
-  X.w = X.s_w;
-  X.c = X.s_c;
+  X.s_B = s_tab[warp];
+  X.s_w = s_tab[warp] + kSmemTable;
+  X.B = X.s_B;
   X.key.k0 = (uint32_t)A.seed;
   X.key.k1 = (uint32_t)(A.seed >> 32);
 
@@ -1175,21 +1386,25 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ssa_kernel(const __grid_c
     X.node_rate = A.dpool + P->rate_off;
     X.edge_parent = A.ipool + P->edge_off;
     X.edge_child = X.edge_parent + P->n_edges;
-    run_replicate(X);
+    run_replicate<T>(X);
   }
 }
 
 int launch_ssa(const RunArgs& args, int grid_blocks, void* stream) {
-  ssa_kernel<<<grid_blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(args);
+  if (args.site_bytes == 2)
+    ssa_kernel<uint16_t><<<grid_blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(args);
+  else
+    ssa_kernel<uint32_t><<<grid_blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(args);
   return (int)cudaGetLastError();
 }
 
 int ssa_max_blocks_per_sm() {
-  int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ssa_kernel, kWarpsPerBlock * 32, 0);
-  return nb;
+  int a = 0, b = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ssa_kernel<uint16_t>, kWarpsPerBlock * 32, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ssa_kernel<uint32_t>, kWarpsPerBlock * 32, 0);
+  return a < b ? a : b;
 }
 
-size_t ssa_smem_bytes() { return sizeof(double) * kWarpsPerBlock * 2 * kSmemClasses; }
+size_t ssa_smem_bytes() { return sizeof(double) * kWarpsPerBlock * (kSmemTable + 32); }
 
 }  // namespace jsb

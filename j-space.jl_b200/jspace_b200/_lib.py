@@ -23,6 +23,8 @@ RULE_CONTACT, RULE_VOTER, RULE_HVOTER, RULE_NONE = 0, 1, 2, 3
 METHOD_RANDOM, METHOD_TREE = 1, 2
 QUIRK_EXCISION_INTENT = 0x1
 QUIRK_DEBUG_SERIAL = 0x100
+QUIRK_DEBUG_EXACT_CLASSES = 0x200
+QUIRK_DEBUG_WIDE_GUARD = 0x400
 OUT_EVENTS, OUT_LATTICE, OUT_LISTS = 0x1, 0x2, 0x4
 EV_DUPLICATE, EV_MUTATION, EV_DEATH, EV_MIGRATION = 0, 1, 2, 3
 EVF_GROUP_START, EVF_DISPLACED, EVF_EXCISION = 0x1, 0x2, 0x4
