@@ -497,6 +497,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     rc = upload_graph(g, opts->device);
     if (rc != JSB_OK) goto done;
     CUDA_TRY(cudaStreamCreate(&stream));
+    CUDA_TRY(cudaDeviceSetLimit(cudaLimitStackSize, 8192));
 
     // ---- sweep points ---------------------------------------------------------------------
     std::vector<DevPoint> hp((size_t)n_points);
@@ -539,19 +540,26 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     // ---- launch geometry ------------------------------------------------------------------
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, opts->device));
-    int blocks_per_sm = ssa_max_blocks_per_sm();
-    if (blocks_per_sm < 1) blocks_per_sm = 1;
-    if (opts->warps_per_sm > 0) blocks_per_sm = std::max(1, std::min(blocks_per_sm, opts->warps_per_sm / kWarpsPerBlock));
-    int64_t want_blocks = (n_local + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    int grid = (int)std::min<int64_t>(want_blocks, (int64_t)prop.multiProcessorCount * blocks_per_sm);
-    const uint64_t slots = (uint64_t)grid * kWarpsPerBlock;
+    RunArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.g.nv = (uint32_t)g->nv;
+    a.site_bytes = g->nv <= 65536 ? 2u : 4u;
+    int wpb = 1;
+    if (ssa_prepare(a, opts->warps_per_sm, &wpb) != 0) { rc = fail(JSB_ECUDA, "cannot configure shared memory for the SSA kernel"); goto done; }
+    // one block per SM; spread small ensembles over all SMs before stacking warps
+    {
+      int64_t per_sm = (n_local + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
+      if (per_sm < wpb) wpb = (int)std::max<int64_t>(1, per_sm);
+    }
+    int grid = (int)std::min<int64_t>((n_local + wpb - 1) / wpb, (int64_t)prop.multiProcessorCount);
+    const uint64_t slots = (uint64_t)grid * wpb;
 
     uint32_t arena_cap = (uint32_t)std::min<uint64_t>(4ull * g->nv + 2ull * kMinListCap * kTab, 0xFFFFFF00ull);
     if (const char* dbg = std::getenv("JSB_DEBUG_ARENA_ENTRIES")) {  // test hook: force compactions
       uint64_t v = std::strtoull(dbg, nullptr, 10);
       arena_cap = (uint32_t)std::max<uint64_t>(v, 4096);  // too small -> JSB_ST_INTERNAL, never UB
     }
-    const uint32_t site_bytes = g->nv <= 65536 ? 2u : 4u;
+    const uint32_t site_bytes = a.site_bytes;
     const WsLayout L = ws_layout((uint32_t)g->nv, arena_cap, site_bytes);
     CUDA_TRY(cudaMalloc(&d_ws, L.total * slots));
 
@@ -585,10 +593,19 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     }
     if (opts->flags & JSB_OUT_LISTS) CUDA_TRY(cudaMalloc(&d_out_lists, sizeof(uint32_t) * 2 * (size_t)g->nv * n_local));
 
-    RunArgs a;
-    std::memset(&a, 0, sizeof a);
     a.g.kind = g->kind; a.g.n1 = g->n1; a.g.n2 = g->n2; a.g.n3 = g->n3; a.g.nv = (uint32_t)g->nv;
     a.g.rowptr = g->d_rowptr; a.g.colidx = g->d_colidx;
+    if (g->kind == 0) {
+      // magic = ceil(2^(28+L) / d), L = ceil(log2 d): (v * magic) >> (28+L) == v / d for every v < 2^28
+      auto magic = [](uint32_t d, uint32_t& m, uint32_t& sh) {
+        uint32_t L = 0;
+        while ((1ull << L) < d) ++L;
+        sh = 28 + L;
+        m = (uint32_t)(((1ull << sh) + d - 1) / d);
+      };
+      magic(g->n1, a.g.m1, a.g.s1);
+      magic(g->n2, a.g.m2, a.g.s2);
+    }
     a.points = d_points; a.dpool = d_dpool; a.ipool = d_ipool;
     a.seed_cand = g->d_cand; a.n_cand = g->d_ncand;
     a.flags = opts->flags; a.seed = opts->seed; a.g_begin = g_begin; a.n_local = n_local; a.reps_per_point = reps_per_point;
@@ -604,7 +621,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     CUDA_TRY(cudaEventCreate(&ev1));
     CUDA_TRY(cudaEventRecord(ev0, stream));
     {
-      int lrc = launch_ssa(a, grid, stream);
+      int lrc = launch_ssa(a, grid, wpb, stream);
       if (lrc != 0) { rc = fail(JSB_ECUDA, "kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc)); goto done; }
     }
     res->launches = 1;

@@ -8,11 +8,14 @@ namespace jsb {
 
 constexpr int kMaxClones = 1000;   // Set(1:1000), src/J_Space.jl:366
 constexpr int kTab = 1024;         // clone-table stride
-constexpr int kSmemTable = 512;    // class boundaries (S+2) kept in the per-warp smem slice
+constexpr int kSmemTable = 1008;   // class boundaries (S+2 <= 1002) in the per-warp smem slice
 constexpr double kGuardEps = 1e-11; // class-selection guard band (relative to λ), DESIGN.md §4
 constexpr int kLogChunk = 1024;    // records per event-log chunk (32 KB)
 constexpr int kMinListCap = 32;    // initial capacity of a ca_subpop list in the arena
-constexpr int kWarpsPerBlock = 4;
+#ifndef JSB_MAXWARPS
+#define JSB_MAXWARPS 12
+#endif
+constexpr int kMaxWarpsPerBlock = JSB_MAXWARPS;  // one block per SM; warps per block chosen at launch
 
 // Draw sites of the draw contract; ctr.w = site << 28 | seq
 enum DrawSite : uint32_t {
@@ -30,6 +33,7 @@ struct DevGraph {
   int kind;  // 0 = implicit lattice (n1 fastest), 1 = CSR
   uint32_t n1, n2, n3;
   uint32_t nv;
+  uint32_t m1, s1, m2, s2;  // v / n1 == (v * m1) >> s1 and yz / n2 == (yz * m2) >> s2 for v < 2^28
   const uint32_t* rowptr;  // [nv+1]
   const uint32_t* colidx;  // 0-based neighbour ids, ascending per row
 };
@@ -63,6 +67,8 @@ struct RunArgs {
   uint64_t ws_stride;
   uint32_t arena_cap;  // entries
   uint32_t site_bytes; // 2 when nv <= 65536, else 4 (storage type of the ordered lists)
+  uint32_t occ_words;  // per-warp shared occupancy bitmask words (0 = lattice too large, use global)
+  uint32_t smem_per_warp;  // bytes of dynamic shared memory per warp
   // outputs
   jsb_summary* summaries;
   jsb_clone* clone_pool;
@@ -111,8 +117,7 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t nv, uint32_t arena_cap, u
 }
 
 // host-callable launch wrapper (jsb_kernels.cu)
-int launch_ssa(const RunArgs& args, int grid_blocks, void* stream);
-int ssa_max_blocks_per_sm();
-size_t ssa_smem_bytes();
+int launch_ssa(const RunArgs& args, int grid_blocks, int warps_per_block, void* stream);
+int ssa_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block);  // fills occ_words / smem_per_warp
 
 }  // namespace jsb

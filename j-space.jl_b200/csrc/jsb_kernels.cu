@@ -33,12 +33,27 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdio>
+
 #include "jsb_device.cuh"
 
 namespace jsb {
 
 #define FULL 0xffffffffu
 constexpr uint32_t kNone = 0xFFFFFFFFu;
+
+// Optional phase profiler (build with -DJSB_PROFILE; debug library only): per-replicate cycle
+// totals per phase, printed by lane 0 for the first replicates.
+#ifdef JSB_PROFILE
+enum { PH_REFOLD, PH_DRAWS, PH_CLASS, PH_EVAL, PH_TIME, PH_BIRTH, PH_DEATH, PH_MIGR, PH_EXC, PH_N };
+#define PROF_DECL long long prof_c[PH_N] = {0}; long long prof_n[PH_N] = {0}; long long prof_t0 = 0; long long prof_fold = 0;
+#define PROF_T0() prof_t0 = clock64()
+#define PROF_ADD(ph) do { long long _t = clock64(); prof_c[ph] += _t - prof_t0; prof_n[ph]++; prof_t0 = _t; } while (0)
+#else
+#define PROF_DECL
+#define PROF_T0()
+#define PROF_ADD(ph)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 and the draw contract
@@ -130,11 +145,14 @@ __device__ __forceinline__ double contract_log(double x) {
 // ---------------------------------------------------------------------------------------------
 // Implicit lattice of Graphs.grid((n1,n2,n3)): vertex = x + y*n1 + z*n1*n2, neighbours ascending:
 // z-1, y-1, x-1, x+1, y+1, z+1.
+__device__ __forceinline__ uint32_t fast_div(uint32_t v, uint32_t magic, uint32_t shift) {
+  return (uint32_t)(((unsigned long long)v * magic) >> shift);  // exact for v < 2^28 (jsb_api.cu)
+}
 __device__ __forceinline__ uint32_t lattice_mask(const DevGraph& g, uint32_t v) {
-  uint32_t x = v % g.n1;
-  uint32_t yz = v / g.n1;
-  uint32_t y = yz % g.n2;
-  uint32_t z = yz / g.n2;
+  uint32_t yz = fast_div(v, g.m1, g.s1);
+  uint32_t x = v - yz * g.n1;
+  uint32_t z = fast_div(yz, g.m2, g.s2);
+  uint32_t y = yz - z * g.n2;
   return (uint32_t)(z > 0) | ((uint32_t)(y > 0) << 1) | ((uint32_t)(x > 0) << 2) | ((uint32_t)(x + 1 < g.n1) << 3) |
          ((uint32_t)(y + 1 < g.n2) << 4) | ((uint32_t)(z + 1 < g.n3) << 5);
 }
@@ -164,15 +182,17 @@ struct Ctx {
   uint32_t* cellid;
   T *Alist, *arena;
   uint32_t *inds, *samp;
-  uint32_t *c_off, *c_len, *c_cap;
+  uint32_t *c_off, *c_len;  // per-warp shared slices [kMaxClones]
+  uint32_t* c_cap;          // global; capacities are powers of two >= kMinListCap
   double* c_alpha;
   uint16_t *c_parent, *c_label;
-  double *g_B, *g_w, *g_c;  // global-memory tables (large S / exact fallback)
-  double *s_B, *s_w;        // per-warp shared slices: boundaries [kSmemTable], staging [32]
-  double* B;                // active boundary table: s_B while S+2 <= kSmemTable, else g_B
+  double *g_w, *g_c;        // global-memory scratch of the exact prob_cum fallback
+  double* B;                // per-warp shared slice: class boundaries [kSmemTable]
+  uint32_t* occ;            // per-warp shared occupancy bitmask (nullptr: test clone[] in global)
   Key key;
   int64_t local_idx;
   int lane;
+  bool track_ids;           // cell ids are only maintained when the log or the lattice is wanted
 };
 
 struct Rep {
@@ -188,6 +208,10 @@ struct Rep {
 __device__ __forceinline__ void mark_dirty(Rep& r, uint32_t clone_idx) {
   r.dirty_from = clone_idx < r.dirty_from ? clone_idx : r.dirty_from;
 }
+
+// shared-memory occupancy bitmask (bit set <=> clone[site] != 0); single-lane updates
+__device__ __forceinline__ void occ_set(uint32_t* occ, uint32_t site) { if (occ) occ[site >> 5] |= 1u << (site & 31); }
+__device__ __forceinline__ void occ_clear(uint32_t* occ, uint32_t site) { if (occ) occ[site >> 5] &= ~(1u << (site & 31)); }
 
 // ---------------------------------------------------------------------------------------------
 // Event log: 32-byte records in pool chunks, rows in the reference's push! order
@@ -236,7 +260,7 @@ __device__ __forceinline__ void log_row(Ctx<T>& X, Rep& r, uint32_t type, uint32
                                         uint32_t label) {
   if (r.log_on) {
     uint32_t slot = (uint32_t)(r.nlog % kLogChunk);
-    if (slot == 0) log_open_chunk(X, r);
+    if (slot == 0) { Ctx<T> xc = X; Rep rc = r; log_open_chunk(xc, rc); r = rc; }
     if (r.log_on && X.lane < 2) {
       jsb_event* dst = X.A->log_pool + (size_t)r.cur_chunk * kLogChunk + slot;
       log_store(dst, X.lane, time, cell, parent, site0 + 1, site2_1, clone, label, type, flags);
@@ -314,7 +338,7 @@ __device__ __noinline__ uint32_t list_find(const T* list, uint32_t len, uint32_t
 template <typename T>
 __device__ __noinline__ void list_remove_at(T* list, uint32_t len, uint32_t idx, int lane) {
   constexpr uint32_t EPV = Vec<T>::EPV;
-  constexpr int U = 4;
+  constexpr int U = 8;
   if (idx + 1 >= len) return;
   const uint32_t last_dst = len - 2;
   const uint32_t g0 = idx / EPV, g1 = last_dst / EPV;
@@ -351,8 +375,10 @@ __device__ __noinline__ void list_remove_at(T* list, uint32_t len, uint32_t idx,
 }
 
 __device__ __forceinline__ uint32_t round_cap(uint32_t c) { return (c + 7u) & ~7u; }
-__device__ __forceinline__ uint32_t gc_cap(uint32_t len) {
-  return len * 2 > (uint32_t)kMinListCap ? round_cap(len * 2) : (uint32_t)kMinListCap;
+__device__ __forceinline__ uint32_t gc_cap(uint32_t len) {  // power of two >= max(min, 2*len)
+  uint32_t c = kMinListCap;
+  while (c < len * 2) c <<= 1;
+  return c;
 }
 
 // Arena compaction, in place, order inside every list untouched.  Pass 1 squeezes the blocks
@@ -395,7 +421,7 @@ __device__ __noinline__ void arena_gc(Ctx<T>& X, Rep& r) {
   uint32_t total = 0;
   for (uint32_t i = lane; i < r.S; i += 32) total += gc_cap(X.c_len[i]);
   for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
-  if (total > X.A->arena_cap) {  // cannot happen when arena_cap >= 2*nv + (kMinListCap + 8)*kTab
+  if (total > X.A->arena_cap) {  // cannot happen when arena_cap >= 4*nv + kMinListCap*kTab
     for (uint32_t i = lane; i < r.S; i += 32) X.c_cap[i] &= 0x7FFFFFFFu;
     __syncwarp();
     r.arena_top = top;
@@ -471,8 +497,16 @@ __device__ __noinline__ bool list_grow(Ctx<T>& X, Rep& r, uint32_t c) {
 
 template <typename T>
 __device__ __forceinline__ bool list_append(Ctx<T>& X, Rep& r, uint32_t c, uint32_t site) {
-  if (X.c_len[c] >= X.c_cap[c]) {
-    if (!list_grow(X, r, c)) return false;
+  {
+    // capacities are powers of two >= kMinListCap, so a list can only be full when its length is
+    // one; only then is the capacity (global memory) looked at
+    const uint32_t len0 = X.c_len[c];
+    if (len0 >= (uint32_t)kMinListCap && (len0 & (len0 - 1)) == 0 && len0 >= X.c_cap[c]) {
+      Ctx<T> xc = X; Rep rc = r;
+      const bool ok = list_grow(xc, rc, c);
+      r = rc;
+      if (!ok) return false;
+    }
   }
   if (X.lane == 0) {
     uint32_t len = X.c_len[c];
@@ -526,37 +560,42 @@ __device__ __noinline__ bool new_clone(Ctx<T>& X, Rep& r, uint32_t parent1, uint
 // B_S = fl(birth + death), B_{S+1} = λ (:696-698).  Re-folded from the first changed clone.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __noinline__ void refold(Ctx<T>& X, Rep& r) {
+__device__ __forceinline__ void refold(Ctx<T>& X, Rep& r) {
   const uint32_t S = r.S;
   const uint32_t from = r.dirty_from < S ? r.dirty_from : S;
   const int lane = X.lane;
-  double* B = (S + 2 <= (uint32_t)kSmemTable) ? X.s_B : X.g_B;
-  if (B != X.B) {  // the table outgrew the shared slice: carry the valid prefix over
-    for (uint32_t i = lane; i < from; i += 32) B[i] = X.B[i];
-    __syncwarp();
-    X.B = B;
-  }
+  double* __restrict__ B = X.B;
+  const double* __restrict__ alpha = X.c_alpha;
+  const uint32_t* __restrict__ clen = X.c_len;
+  // phase A: B[i] <- w_i = α_i·n_i for every i >= from (parallel; all loads in flight at once)
+  for (uint32_t i = from + lane; i < S; i += 32) B[i] = alpha[i] * (double)clen[i];  // :693
+  __syncwarp();
+  // phase B: in-place sequential left fold (the reference's `sum`), every lane redundantly
   double acc = from ? B[from - 1] : 0.0;  // 0.0 + w_0 == w_0 exactly
-  for (uint32_t base = from; base < S; base += 32) {
-    uint32_t i = base + lane;
-    double w = 0.0;
-    if (i < S) w = X.c_alpha[i] * (double)X.c_len[i];  // :693
-    X.s_w[lane] = w;
+  uint32_t i = from;
+  for (; i < S && (i & 1u); ++i) {
+    acc = acc + B[i];
     __syncwarp();
-    const uint32_t cnt = S - base < 32u ? S - base : 32u;
-    if (cnt == 32u) {
+    if (lane == 0) B[i] = acc;
+  }
+  for (; i + 32 <= S; i += 32) {
+    double mine = 0.0;
 #pragma unroll
-      for (uint32_t l = 0; l < 32u; ++l) {
-        acc = acc + X.s_w[l];
-        if (lane == 0) B[base + l] = acc;
-      }
-    } else {
-      for (uint32_t l = 0; l < cnt; ++l) {
-        acc = acc + X.s_w[l];
-        if (lane == 0) B[base + l] = acc;
-      }
+    for (uint32_t l = 0; l < 32u; l += 2) {
+      double2 ww = *reinterpret_cast<const double2*>(B + i + l);
+      acc = acc + ww.x;
+      if ((uint32_t)lane == l) mine = acc;
+      acc = acc + ww.y;
+      if ((uint32_t)lane == l + 1) mine = acc;
     }
     __syncwarp();
+    B[i + lane] = mine;
+    __syncwarp();
+  }
+  for (; i < S; ++i) {
+    acc = acc + B[i];
+    __syncwarp();
+    if (lane == 0) B[i] = acc;
   }
   const double death = X.P->rate_death * (double)r.n;     // :696
   const double M = X.P->rate_migration * (double)r.n;     // :697
@@ -577,9 +616,12 @@ __device__ __noinline__ void refold(Ctx<T>& X, Rep& r) {
 // Exact prob_cum = cumsum(vcat(α_subpop ./ λ, death/λ, M/λ)) (:703-718) in Julia's
 // accumulate_pairwise! order, stored as its running maximum so that a lower bound equals
 // findfirst(k .<= prob_cum).  Only built when some k falls inside the guard band.
-__device__ double acc_pairwise(double* __restrict__ v, double* __restrict__ c, double s, int i1, int n, double& mx,
-                               int lane) {
-  if (n < 128) {
+// Depth-bounded form of the recursion (n <= 1001 needs at most 3 levels of halving before every
+// block is shorter than 128), so the stack size is known at compile time.
+template <int DEPTH>
+__device__ __forceinline__ double acc_pairwise(double* __restrict__ v, double* __restrict__ c, double s, int i1, int n,
+                                               double& mx, int lane) {
+  if (DEPTH == 0 || n < 128) {
     double s_ = v[i1];
     double cv = s + s_;
     mx = cv > mx ? cv : mx;
@@ -593,8 +635,8 @@ __device__ double acc_pairwise(double* __restrict__ v, double* __restrict__ c, d
     return s_;
   }
   int n2 = n >> 1;
-  double sl = acc_pairwise(v, c, s, i1, n2, mx, lane);
-  double sr = acc_pairwise(v, c, s + sl, i1 + n2, n - n2, mx, lane);
+  double sl = acc_pairwise<(DEPTH > 0 ? DEPTH - 1 : 0)>(v, c, s, i1, n2, mx, lane);
+  double sr = acc_pairwise<(DEPTH > 0 ? DEPTH - 1 : 0)>(v, c, s + sl, i1 + n2, n - n2, mx, lane);
   return sl + sr;
 }
 
@@ -613,7 +655,8 @@ __device__ __noinline__ void build_exact_table(Ctx<T>& X, Rep& r) {
   double v1 = w[0];
   if (X.lane == 0) c[0] = v1;
   double mx = v1;
-  acc_pairwise(w, c, v1, 1, S + 1, mx, X.lane);
+  static_assert(kMaxClones + 1 < (128 << 4), "pairwise depth");
+  acc_pairwise<4>(w, c, v1, 1, S + 1, mx, X.lane);
   __syncwarp();
   r.exact_valid = true;
 }
@@ -630,61 +673,161 @@ struct Eval {
   bool effective;
 };
 
-// first i in [0, n) with !(tab[i] < key); n when none
+// first i in [0, n) with !(tab[i] < key); n when none.  All values are non-negative doubles, so
+// the IEEE bit patterns order like the numbers and the search runs on integer compares (an fp64
+// compare costs a full ~32-cycle fp64 pipe round trip on this part); fixed 10 steps, no branches.
 __device__ __forceinline__ uint32_t lower_bound(const double* tab, uint32_t n, double key) {
-  uint32_t lo = 0, len = n;
-  while (len > 0) {
-    uint32_t half = len >> 1;
-    if (tab[lo + half] < key) { lo += half + 1; len -= half + 1; } else { len = half; }
+  const unsigned long long* t = reinterpret_cast<const unsigned long long*>(tab);
+  const unsigned long long k = (unsigned long long)__double_as_longlong(key);
+  uint32_t lo = 0;  // number of leading entries known to be < key
+#pragma unroll
+  for (uint32_t step = 512; step > 0; step >>= 1) {
+    uint32_t probe = lo + step;
+    if (probe <= n && t[probe - 1] < k) lo = probe;
   }
   return lo;
 }
 
+// Phase 1 of a speculative evaluation: class -> member list -> x -> the dividing/dying/moving
+// cell.  Written branch-light so that the sub-batches of one lane interleave (ILP).
 template <typename T>
-__device__ __forceinline__ Eval evaluate_class(const Ctx<T>& X, const Rep& r, uint64_t q, uint32_t cls, uint64_t w_cell,
-                                               uint64_t w_nbr) {
-  Eval e;
-  e.cls = cls; e.x = 0; e.cell = 0; e.pos = 0; e.occ = 0; e.effective = false;
+__device__ __forceinline__ void eval_member(const Ctx<T>& X, const Rep& r, uint64_t q, uint32_t cls, uint64_t w_cell,
+                                            uint32_t& x, uint32_t& cell, bool& valid) {
   const uint32_t S = r.S;
-  if (cls >= S + 2) return e;  // reference: findfirst -> nothing; contract: null iteration
-  const T* list;
-  uint32_t llen;
-  if (cls < S) { list = X.arena + X.c_off[cls]; llen = X.c_len[cls]; } else { list = X.Alist; llen = r.n; }
-  if (llen == 0) return e;     // rand(1:0) throws in the reference; contract: null iteration
-  e.x = bounded(X.key, w_cell, llen, q, DS_CELL_NBR, 0, 0);  // :727 / :746 / :762
-  e.cell = (uint32_t)list[e.x];
-  if (cls == S) { e.effective = true; return e; }  // death :744-759 needs no neighbour
+  const bool is_birth = cls < S;
+  const uint32_t ci = is_birth ? cls : 0u;
+  const uint32_t off = X.c_off[ci], cl = X.c_len[ci];
+  const T* list = is_birth ? X.arena + off : X.Alist;
+  const uint32_t llen = is_birth ? cl : r.n;
+  // cls >= S+2: findfirst -> nothing in the reference; llen == 0: rand(1:0) throws.  Contract:
+  // both are null iterations.
+  valid = (cls < S + 2) && (llen > 0);
+  x = 0;
+  cell = 0;
+  if (valid) {
+    x = bounded(X.key, w_cell, llen, q, DS_CELL_NBR, 0, 0);  // :727 / :746 / :762
+    cell = (uint32_t)list[x];
+  }
+}
+
+// Phase 2: neighbour draw, occupancy test, contact rule.  Returns whether the iteration changes
+// state.
+template <typename T>
+__device__ __forceinline__ bool eval_target(const Ctx<T>& X, const Rep& r, uint64_t q, uint32_t cls, uint32_t cell,
+                                            bool valid, uint64_t w_nbr, uint32_t& pos) {
+  const uint32_t S = r.S;
+  pos = 0;
+  if (!valid) return false;
+  if (cls == S) return true;  // death :744-759 needs no neighbour
   const DevGraph& g = X.A->g;
   uint32_t deg, mask = 0, row0 = 0;
-  if (g.kind == 0) { mask = lattice_mask(g, e.cell); deg = (uint32_t)__popc(mask); }
-  else { row0 = g.rowptr[e.cell]; deg = g.rowptr[e.cell + 1] - row0; }
-  if (deg == 0) return e;     // rand on an empty neighbour list throws; contract: null iteration
-  uint32_t j = bounded(X.key, w_nbr, deg, q, DS_CELL_NBR, 0, 1);  // :730 / :764
-  e.pos = (g.kind == 0) ? lattice_pick(g, e.cell, mask, j) : g.colidx[row0 + j];
-  e.occ = X.clone[e.pos];
-  if (cls == S + 1) { e.effective = (e.occ == 0); return e; }  // migration :732
-  bool rule = true;  // :767-786
+  if (g.kind == 0) { mask = lattice_mask(g, cell); deg = (uint32_t)__popc(mask); }
+  else { row0 = g.rowptr[cell]; deg = g.rowptr[cell + 1] - row0; }
+  if (deg == 0) return false;  // rand on an empty neighbour list throws; contract: null iteration
+  const uint32_t j = bounded(X.key, w_nbr, deg, q, DS_CELL_NBR, 0, 1);  // :730 / :764
+  pos = (g.kind == 0) ? lattice_pick(g, cell, mask, j) : g.colidx[row0 + j];
   const int model = X.P->rule;
-  if (model == JSB_RULE_CONTACT) rule = (e.occ == 0);
-  else if (model == JSB_RULE_VOTER) rule = !(e.occ != 0 && e.occ == cls + 1);
-  else if (model == JSB_RULE_HVOTER) rule = !(e.occ != 0 && X.c_alpha[cls] <= X.c_alpha[e.occ - 1]);
-  e.effective = rule;
-  return e;
+  uint32_t occ;
+  if (X.occ) {
+    // `pos ∈ cs_alive` from the shared bitmask; the clone id itself is only needed when a voter
+    // rule may displace the occupant
+    const bool occupied = (X.occ[pos >> 5] >> (pos & 31)) & 1u;
+    occ = occupied ? ((model == JSB_RULE_CONTACT || cls == S + 1) ? 1u : (uint32_t)X.clone[pos]) : 0u;
+  } else {
+    occ = X.clone[pos];
+  }
+  if (cls == S + 1) return occ == 0;  // migration :732
+  bool rule = true;                   // :767-786
+  if (model == JSB_RULE_CONTACT) rule = (occ == 0);
+  else if (model == JSB_RULE_VOTER) rule = !(occ != 0 && occ == cls + 1);
+  else if (model == JSB_RULE_HVOTER) rule = !(occ != 0 && X.c_alpha[cls] <= X.c_alpha[occ - 1]);
+  return rule;
+}
+
+// One speculative window of U sub-batches: lane l of sub-batch u evaluates iteration
+// it + 1 + 32u + l against the current state.  effm[u] = ballot of state-changing lanes.
+// Measured on B200 (C2 ensemble): windows of 2-4 sub-batches per lane cut single-replicate latency
+// by only ~8 % and cost 30-60 % throughput in wasted speculation, so the window stays at one
+// sub-batch; the multi-sub-batch path is kept for experiments (kAdaptiveWindow).
+constexpr int kMaxSub = 4;
+constexpr bool kAdaptiveWindow = false;
+template <typename T, int U>
+__device__ __forceinline__ void batch_eval(Ctx<T>& X, Rep& r, bool force_exact, uint32_t wmask, double (&dtv)[kMaxSub],
+                                           uint32_t (&effm)[kMaxSub], uint32_t (&cls)[kMaxSub], uint32_t (&xx)[kMaxSub],
+                                           uint32_t (&cell)[kMaxSub], uint32_t (&pos)[kMaxSub]) {
+  const int lane = X.lane;
+  const uint32_t nb = r.S + 2;
+  uint64_t wc[U], wd[U];
+  bool unc[U];
+  bool unc_any = false;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint64_t q = r.it + 1 + (uint64_t)(u * 32 + lane);
+    uint64_t wa, wb;
+    draw_block(X.key, q, 0, DS_TIME_CLASS, 0, wa, wb);
+    draw_block(X.key, q, 0, DS_CELL_NBR, 0, wc[u], wd[u]);
+    dtv[u] = (-contract_log(u01_open(wa))) * r.theta;  // :699
+    // event class: k·λ against the folded boundaries
+    const double key = u01_53(wb) * r.lambda;          // :721
+    const uint32_t c = lower_bound(X.B, nb, key);
+    const uint32_t cc = c < nb ? c : nb - 1;
+    unc[u] = force_exact || c >= nb || (X.B[cc] - key <= r.guard) || (cc > 0 && key - X.B[cc - 1] <= r.guard);
+    unc_any = unc_any || unc[u];
+    cls[u] = c;
+  }
+  if (__ballot_sync(FULL, unc_any) & wmask) {  // some k is inside the guard band: exact prob_cum table
+    if (!r.exact_valid) { Ctx<T> xc = X; Rep rc = r; build_exact_table(xc, rc); r = rc; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (unc[u]) {
+        const uint64_t q = r.it + 1 + (uint64_t)(u * 32 + lane);
+        uint64_t wa, wb;
+        draw_block(X.key, q, 0, DS_TIME_CLASS, 0, wa, wb);
+        cls[u] = lower_bound(X.g_c, nb, u01_53(wb));  // findfirst(k .<= prob_cum) :722-723
+      }
+    }
+  }
+  bool valid[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint64_t q = r.it + 1 + (uint64_t)(u * 32 + lane);
+    eval_member(X, r, q, cls[u], wc[u], xx[u], cell[u], valid[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const uint64_t q = r.it + 1 + (uint64_t)(u * 32 + lane);
+    const bool eff = eval_target(X, r, q, cls[u], cell[u], valid[u], wd[u], pos[u]);
+    effm[u] = __ballot_sync(FULL, eff) & wmask;
+  }
+}
+
+// sequential t += dt over lanes 0..last of one sub-batch (:701)
+__device__ __forceinline__ double time_chain(double t, double dt, uint32_t last) {
+  uint32_t l = 0;
+  for (; l + 4 <= last + 1; l += 4) {  // shuffles issue back to back, the adds stay sequential
+    double d0 = __shfl_sync(FULL, dt, (int)l), d1 = __shfl_sync(FULL, dt, (int)l + 1);
+    double d2 = __shfl_sync(FULL, dt, (int)l + 2), d3 = __shfl_sync(FULL, dt, (int)l + 3);
+    t = t + d0; t = t + d1; t = t + d2; t = t + d3;
+  }
+  for (; l <= last; ++l) t = t + __shfl_sync(FULL, dt, (int)l);
+  return t;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Event application (whole warp cooperates; control flow is warp-uniform)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __noinline__ void apply_migration(Ctx<T>& X, Rep& r, const Eval& e) {  // :733-741, migration_cell :592-613
-  uint32_t cid = X.cellid[e.cell];
+__device__ __forceinline__ void apply_migration(Ctx<T>& X, Rep& r, const Eval& e) {  // :733-741, migration_cell :592-613
+  uint32_t cid = X.track_ids ? X.cellid[e.cell] : 0u;
   uint32_t cl = X.clone[e.cell];
   __syncwarp();
   if (X.lane == 0) {
     X.clone[e.cell] = 0;
     X.clone[e.pos] = (uint16_t)cl;
-    X.cellid[e.pos] = cid;
+    if (X.track_ids) X.cellid[e.pos] = cid;
     X.Alist[r.n] = (T)e.pos;  // push!(cs_alive, pos)
+    occ_clear(X.occ, e.cell);
+    occ_set(X.occ, e.pos);
   }
   __syncwarp();
   log_row(X, r, JSB_EV_MIGRATION, JSB_EVF_GROUP_START, r.t, cid, 0, e.pos, e.cell + 1, cl, 0);
@@ -696,12 +839,12 @@ __device__ __noinline__ void apply_migration(Ctx<T>& X, Rep& r, const Eval& e) {
 }
 
 template <typename T>
-__device__ __noinline__ void apply_death(Ctx<T>& X, Rep& r, const Eval& e) {  // :746-759, cell_death :574-586
-  uint32_t cid = X.cellid[e.cell];
+__device__ __forceinline__ void apply_death(Ctx<T>& X, Rep& r, const Eval& e) {  // :746-759, cell_death :574-586
+  uint32_t cid = X.track_ids ? X.cellid[e.cell] : 0u;
   uint32_t cl = X.clone[e.cell];
   __syncwarp();
   log_row(X, r, JSB_EV_DEATH, JSB_EVF_GROUP_START, r.t, cid, 0, e.cell, 0, cl, 0);
-  if (X.lane == 0) X.clone[e.cell] = 0;
+  if (X.lane == 0) { X.clone[e.cell] = 0; occ_clear(X.occ, e.cell); }
   __syncwarp();
   list_remove_at<T>(X.Alist, r.n, e.x, X.lane);
   list_remove_value(X, cl - 1, e.cell);
@@ -712,7 +855,7 @@ __device__ __noinline__ void apply_death(Ctx<T>& X, Rep& r, const Eval& e) {  //
 }
 
 // j-th (0-based) unused label of 1..1000; lane l owns labels 32l..32l+31
-__device__ __noinline__ uint32_t pick_label(uint32_t& used_w, uint32_t j, int lane) {
+__device__ __noinline__ uint32_t pick_label(uint32_t used_w, uint32_t j, int lane) {
   uint32_t freew = ~used_w;
   uint32_t cnt = (uint32_t)__popc(freew);
   uint32_t incl = cnt;
@@ -729,7 +872,6 @@ __device__ __noinline__ uint32_t pick_label(uint32_t& used_w, uint32_t j, int la
     for (uint32_t q = 0; q < k; ++q) m &= m - 1;
     uint32_t bit = (uint32_t)__ffs(m) - 1u;
     lab = (uint32_t)lane * 32u + bit;
-    used_w |= 1u << bit;
   }
   uint32_t who = __ballot_sync(FULL, mine);
   return __shfl_sync(FULL, lab, __ffs(who) - 1);
@@ -770,7 +912,7 @@ __device__ __noinline__ int tree_child(const Ctx<T>& X, const Rep& r, uint32_t s
 // cell_birth :320-416 / :419-537 plus the caller's bookkeeping :803-808.  Returns false when the
 // replicate must stop.
 template <typename T>
-__device__ __noinline__ bool apply_birth(Ctx<T>& X, Rep& r, const Eval& e) {
+__device__ __forceinline__ bool apply_birth(Ctx<T>& X, Rep& r, const Eval& e) {
   const DevPoint& P = *X.P;
   const uint32_t sp = e.cls + 1;  // :Subpop of the dividing cell (== min)
   uint64_t wa, wb;
@@ -779,7 +921,7 @@ __device__ __noinline__ bool apply_birth(Ctx<T>& X, Rep& r, const Eval& e) {
   int child_node = -1;
   bool driver;
   if (P.method == JSB_METHOD_TREE) {
-    if (rr <= P.mu) child_node = tree_child(X, r, sp);  // :448
+    if (rr <= P.mu) { Ctx<T> xc = X; Rep rc = r; child_node = tree_child(xc, rc, sp); }  // :448
     driver = child_node >= 0;                            // :476
   } else {
     driver = !(rr > P.mu);  // :348
@@ -789,8 +931,8 @@ __device__ __noinline__ bool apply_birth(Ctx<T>& X, Rep& r, const Eval& e) {
     return false;
   }
   uint32_t first_flag = JSB_EVF_GROUP_START;
-  if (e.occ != 0) {  // :335-338 displacement (voter rules)
-    uint32_t pid = X.cellid[e.pos];
+  if (e.occ != 0) {  // :335-338 displacement (voter rules); e.occ was read by the caller
+    uint32_t pid = X.track_ids ? X.cellid[e.pos] : 0u;
     __syncwarp();
     list_remove_value(X, e.occ - 1, e.pos);
     mark_dirty(r, e.occ - 1);
@@ -800,14 +942,13 @@ __device__ __noinline__ bool apply_birth(Ctx<T>& X, Rep& r, const Eval& e) {
   }
   const uint32_t nid = r.next_id, nid2 = r.next_id + 1;  // uuid1 ×2 :340-341
   r.next_id += 2;
-  const uint32_t parent = X.cellid[e.cell];
+  const uint32_t parent = X.track_ids ? X.cellid[e.cell] : 0u;
   __syncwarp();
   if (!driver) {  // :351-363 / :477-490
     log_row(X, r, JSB_EV_DUPLICATE, first_flag, r.t, nid, parent, e.cell, 0, sp, 0);
     log_row(X, r, JSB_EV_DUPLICATE, 0, r.t, nid2, parent, e.pos, 0, sp, 0);
     if (X.lane == 0) {
-      X.cellid[e.cell] = nid;
-      X.cellid[e.pos] = nid2;
+      if (X.track_ids) { X.cellid[e.cell] = nid; X.cellid[e.pos] = nid2; }
       X.clone[e.pos] = (uint16_t)sp;
     }
     __syncwarp();
@@ -825,6 +966,7 @@ __device__ __noinline__ bool apply_birth(Ctx<T>& X, Rep& r, const Eval& e) {
       draw_block(X.key, r.it, 0, DS_LABEL, 0, a, b);
       uint32_t j = bounded(X.key, a, n_free, r.it, DS_LABEL, 0, 0);  // :371
       label = pick_label(r.used_w, j, X.lane);
+      if ((uint32_t)X.lane == (label >> 5)) r.used_w |= 1u << (label & 31u);
       double z = contract_randn(X.key, r.it);  // :565-566
       nalpha = X.c_alpha[sp - 1] + fabs(P.adv_mean + P.adv_std * z);
     }
@@ -834,27 +976,25 @@ __device__ __noinline__ bool apply_birth(Ctx<T>& X, Rep& r, const Eval& e) {
     log_row(X, r, JSB_EV_DUPLICATE, 0, r.t, nid, parent, coin ? e.cell : e.pos, 0, sp, 0);
     if (coin) {  // :392-400
       if (X.lane == 0) {
-        X.cellid[e.cell] = nid;
-        X.cellid[e.pos] = nid2;
+        if (X.track_ids) { X.cellid[e.cell] = nid; X.cellid[e.pos] = nid2; }
         X.clone[e.pos] = (uint16_t)nsp;
       }
       __syncwarp();
-      if (!new_clone(X, r, sp, label, nalpha, e.pos)) return false;
+      { Ctx<T> xc = X; Rep rc = r; const bool ok = new_clone(xc, rc, sp, label, nalpha, e.pos); r = rc; if (!ok) return false; }
     } else {  // :402-412
       if (X.lane == 0) {
-        X.cellid[e.pos] = nid;
+        if (X.track_ids) { X.cellid[e.pos] = nid; X.cellid[e.cell] = nid2; }
         X.clone[e.pos] = (uint16_t)sp;
-        X.cellid[e.cell] = nid2;
         X.clone[e.cell] = (uint16_t)nsp;
       }
       __syncwarp();
       if (!list_append(X, r, sp - 1, e.pos)) return false;
       list_remove_value(X, sp - 1, e.cell);
-      if (!new_clone(X, r, sp, label, nalpha, e.cell)) return false;
+      { Ctx<T> xc = X; Rep rc = r; const bool ok = new_clone(xc, rc, sp, label, nalpha, e.cell); r = rc; if (!ok) return false; }
     }
   }
   if (e.occ == 0) {  // :803-806
-    if (X.lane == 0) X.Alist[r.n] = (T)e.pos;
+    if (X.lane == 0) { X.Alist[r.n] = (T)e.pos; occ_set(X.occ, e.pos); }
     __syncwarp();
     r.n += 1;
     mark_dirty(r, r.S);  // death and migration weights changed (B_S, B_{S+1})
@@ -950,7 +1090,7 @@ __device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double
       uint32_t i = b + lane;
       if (i < m) {
         uint32_t site = samp[done + i];
-        uint32_t cid = X.cellid[site];
+        uint32_t cid = X.track_ids ? X.cellid[site] : 0u;
         uint32_t cl = X.clone[site];
         if (r.log_on) {
           jsb_event* dst = X.A->log_pool + (size_t)r.cur_chunk * kLogChunk + (uint32_t)(r.nlog % kLogChunk) + i;
@@ -965,6 +1105,9 @@ __device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double
   }
   __syncwarp();
   for (uint32_t i = lane; i < k; i += 32) X.clone[samp[i]] = 0;
+  __syncwarp();
+  if (X.occ && lane == 0)
+    for (uint32_t i = 0; i < k; ++i) occ_clear(X.occ, samp[i]);
   __syncwarp();
   // stable compaction of cs_alive and of every ca_subpop list (== the sequence of filter! calls)
   {
@@ -1012,6 +1155,8 @@ __device__ __noinline__ void seed_replicate(Ctx<T>& X, Rep& r) {
   const DevGraph& g = X.A->g;
   const int lane = X.lane;
   for (uint32_t i = lane; i < (g.nv + 1) / 2; i += 32) reinterpret_cast<uint32_t*>(X.clone)[i] = 0;
+  if (X.occ)
+    for (uint32_t i = lane; i < X.A->occ_words; i += 32) X.occ[i] = 0;
   __syncwarp();
   uint32_t n0 = 0;
   if (P.n_start == 1) {
@@ -1027,6 +1172,7 @@ __device__ __noinline__ void seed_replicate(Ctx<T>& X, Rep& r) {
         X.clone[v0] = 1;
         X.cellid[v0] = 1;
         X.Alist[0] = (T)v0;
+        occ_set(X.occ, v0);
       }
       n0 = 1;
     }
@@ -1047,6 +1193,7 @@ __device__ __noinline__ void seed_replicate(Ctx<T>& X, Rep& r) {
         ++cnt;
         X.clone[pos] = 1;
         X.cellid[pos] = (uint32_t)i + 1;
+        occ_set(X.occ, pos);
       }
       for (uint32_t q = 0; q < cnt; ++q) X.Alist[q] = (T)X.samp[q];
     }
@@ -1207,7 +1354,7 @@ __device__ __noinline__ SlowOut slow_scan(const Ctx<T>& X, const Rep& r, double 
 // One replicate
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__device__ void run_replicate(Ctx<T>& X) {
+__device__ __forceinline__ void run_replicate(Ctx<T>& X) {
   const RunArgs& A = *X.A;
   const DevPoint& P = *X.P;
   const int lane = X.lane;
@@ -1220,75 +1367,91 @@ __device__ void run_replicate(Ctx<T>& X) {
   r.log_on = (A.flags & JSB_OUT_EVENTS) != 0;
   r.exact_valid = false;
   r.dirty_from = 0;
-  X.B = X.s_B;
-  seed_replicate(X, r);
+  { Ctx<T> xc = X; Rep rc = r; seed_replicate(xc, rc); r = rc; }
 
   const bool intent = (P.quirks & JSB_QUIRK_EXCISION_INTENT) != 0;
   const bool force_exact = (P.quirks & JSB_QUIRK_DEBUG_EXACT_CLASSES) != 0;
   const uint32_t width = (P.quirks & JSB_QUIRK_DEBUG_SERIAL) ? 1u : 32u;
   const uint32_t wmask = width == 32 ? FULL : ((1u << width) - 1u);
   const uint32_t nv = A.g.nv;
+  uint32_t Ucur = 1;  // sub-batches per speculative window (1, 2 or 4), adapted to the run length
 
+  PROF_DECL
   for (;;) {
     if (!(r.t < P.Tf && r.n > 0)) {  // loop test :687-688
       if (P.rate_death == 0.0 && r.n == nv) r.status = JSB_ST_NONTERMINATING;
       break;
     }
-    if (r.dirty_from != kNone) refold(X, r);
+    PROF_T0();
+#ifdef JSB_PROFILE
+    if (r.dirty_from != kNone) prof_fold += (long long)r.S - (long long)(r.dirty_from < r.S ? r.dirty_from : r.S);
+#endif
+    if (r.dirty_from != kNone) { refold(X, r); PROF_ADD(PH_REFOLD); }
 
-    // ---- 32 iterations' worth of draws -------------------------------------------------------
-    const uint64_t q = r.it + 1 + (uint64_t)lane;
-    uint64_t wa, wb, wc, wd;
-    draw_block(X.key, q, 0, DS_TIME_CLASS, 0, wa, wb);
-    draw_block(X.key, q, 0, DS_CELL_NBR, 0, wc, wd);
-    const double dt = (-contract_log(u01_open(wa))) * r.theta;  // :699
+    // ---- speculative window: Ucur sub-batches of 32 iterations ----------------------------------
+    double dtv[kMaxSub];
+    uint32_t effm[kMaxSub], cls[kMaxSub], xx[kMaxSub], cell[kMaxSub], pos[kMaxSub];
+    if (!kAdaptiveWindow || Ucur == 1) batch_eval<T, 1>(X, r, force_exact, wmask, dtv, effm, cls, xx, cell, pos);
+    else if (Ucur == 2) batch_eval<T, 2>(X, r, force_exact, wmask, dtv, effm, cls, xx, cell, pos);
+    else batch_eval<T, 4>(X, r, force_exact, wmask, dtv, effm, cls, xx, cell, pos);
+    PROF_ADD(PH_EVAL);
 
-    // ---- event class: k·λ against the folded boundaries, exact table inside the guard band ----
-    const double k = u01_53(wb);  // :721
-    uint32_t cls;
-    {
-      const double key = k * r.lambda;
-      const uint32_t nb = r.S + 2;
-      cls = lower_bound(X.B, nb, key);
-      bool unc = force_exact || cls >= nb || (X.B[cls] - key <= r.guard) || (cls > 0 && key - X.B[cls - 1] <= r.guard);
-      if (__ballot_sync(FULL, unc) & wmask) {
-        if (!r.exact_valid) build_exact_table(X, r);
-        if (unc) cls = lower_bound(X.g_c, nb, k);  // findfirst(k .<= prob_cum) :722-723
-      }
-    }
-    Eval e = evaluate_class(X, r, q, cls, wc, wd);
-    const uint32_t effmask = __ballot_sync(FULL, e.effective) & wmask;
-    const uint32_t jE = effmask ? (uint32_t)__ffs(effmask) - 1u : width - 1u;
+    // first state-changing iteration of the window (sub-batch ustar, lane jE)
+    uint32_t ustar = Ucur - 1, jE = width - 1u;
+    bool found = false;
+#pragma unroll
+    for (int u = kMaxSub - 1; u >= 0; --u)
+      if ((uint32_t)u < Ucur && effm[u]) { ustar = (uint32_t)u; jE = (uint32_t)__ffs(effm[u]) - 1u; found = true; }
 
-    // ---- time chain over the lanes that may commit --------------------------------------------
+    // ---- time chain over the iterations that may commit -----------------------------------------
     double tend = r.t;
-    for (uint32_t l = 0; l <= jE; ++l) tend = tend + __shfl_sync(FULL, dt, (int)l);  // :701
+#pragma unroll
+    for (int u = 0; u < kMaxSub; ++u)
+      if ((uint32_t)u <= ustar && (uint32_t)u < Ucur) tend = time_chain(tend, dtv[u], (uint32_t)u == ustar ? jE : 31u);
 
-    // ---- can anything other than the event at jE happen in (t, tend]? --------------------------
-    bool slow = !(tend < P.Tf);
-    if (P.max_iter && r.it + jE + 1 > P.max_iter) slow = true;
-    if (r.snap_idx < P.n_snap && tend > X.tsnap[r.snap_idx]) slow = true;
-    if (P.n_bott > 0) {
-      if (intent) {
-        if (r.bott_id > 0) { double tb = X.tb[r.bott_id - 1]; if (tb > r.t && tb <= tend) slow = true; }
-      } else if (P.method == JSB_METHOD_TREE) {
-        if (r.it + 1 < (uint64_t)P.n_bott) slow = true;
-        else { double tb = X.tb[P.n_bott - 1]; if (tb > r.t && tb <= tend) slow = true; }
-      } else {
-        double tb = X.tb[0]; if (tb > r.t && tb <= tend) slow = true;
+    // ---- can anything other than that one event happen in (t, tend]? ---------------------------
+    auto touches = [&](double t1, uint64_t n_commit) -> bool {
+      bool sl = !(t1 < P.Tf);
+      if (P.max_iter && r.it + n_commit > P.max_iter) sl = true;
+      if (r.snap_idx < P.n_snap && t1 > X.tsnap[r.snap_idx]) sl = true;
+      if (P.n_bott > 0) {
+        if (intent) {
+          if (r.bott_id > 0) { double tb = X.tb[r.bott_id - 1]; if (tb > r.t && tb <= t1) sl = true; }
+        } else if (P.method == JSB_METHOD_TREE) {
+          if (r.it + 1 < (uint64_t)P.n_bott) sl = true;
+          else { double tb = X.tb[P.n_bott - 1]; if (tb > r.t && tb <= t1) sl = true; }
+        } else {
+          double tb = X.tb[0]; if (tb > r.t && tb <= t1) sl = true;
+        }
       }
+      return sl;
+    };
+    bool slow = touches(tend, (uint64_t)ustar * 32u + jE + 1u);
+    if (slow && Ucur > 1) {  // retry with the first sub-batch only
+      ustar = 0;
+      found = effm[0] != 0;
+      jE = found ? (uint32_t)__ffs(effm[0]) - 1u : 31u;
+      tend = time_chain(r.t, dtv[0], jE);
+      slow = touches(tend, (uint64_t)jE + 1u);
+      Ucur = 1;
+    } else if (kAdaptiveWindow && width == 32u) {
+      // adapt the window to the observed run length
+      if (!found) Ucur = Ucur < (uint32_t)kMaxSub ? Ucur * 2 : (uint32_t)kMaxSub;
+      else Ucur = ustar == 0 ? 1u : (ustar == 1 ? 2u : (uint32_t)kMaxSub);
     }
 
     uint32_t j = jE;
-    bool do_event = effmask != 0;
+    bool do_event = found;
     bool do_snap = false, do_bott = false;
     double tb_fire = 0.0, ratio_fire = 0.0;
 
     if (!slow) {
-      r.it += jE + 1;
+      r.it += (uint64_t)ustar * 32u + jE + 1u;
       r.t = tend;
     } else {
-      SlowOut o = slow_scan(X, r, dt, e.effective, jE, wmask, q);
+      SlowOut o;
+      const bool eff0 = (effm[0] >> lane) & 1u;
+      { Ctx<T> xc = X; Rep rc = r; o = slow_scan(xc, rc, dtv[0], eff0, jE, wmask, r.it + 1 + (uint64_t)lane); }
       j = o.j;
       if (o.stop || o.maxit) {
         r.it += j;
@@ -1306,6 +1469,7 @@ __device__ void run_replicate(Ctx<T>& X) {
       ratio_fire = o.ratio;
     }
 
+    PROF_ADD(PH_TIME);
     if (do_snap) {  // :708-714
       if (lane == 0 && A.snaps) {
         jsb_snapshot s;
@@ -1318,34 +1482,56 @@ __device__ void run_replicate(Ctx<T>& X) {
     bool keep_going = true;
     if (do_event) {
       Eval ej;
-      ej.cls = __shfl_sync(FULL, e.cls, (int)j);
-      ej.x = __shfl_sync(FULL, e.x, (int)j);
-      ej.cell = __shfl_sync(FULL, e.cell, (int)j);
-      ej.pos = __shfl_sync(FULL, e.pos, (int)j);
-      ej.occ = __shfl_sync(FULL, e.occ, (int)j);
+      ej.cls = ej.x = ej.cell = ej.pos = 0;
+#pragma unroll
+      for (int u = 0; u < kMaxSub; ++u)
+        if ((uint32_t)u == ustar) {
+          ej.cls = __shfl_sync(FULL, cls[u], (int)j);
+          ej.x = __shfl_sync(FULL, xx[u], (int)j);
+          ej.cell = __shfl_sync(FULL, cell[u], (int)j);
+          ej.pos = __shfl_sync(FULL, pos[u], (int)j);
+        }
+      // the occupant's clone id matters only when a voter rule displaces it
+      ej.occ = (ej.cls < r.S && P.rule != JSB_RULE_CONTACT) ? (uint32_t)X.clone[ej.pos] : 0u;
       ej.effective = true;
-      if (ej.cls == r.S + 1) apply_migration(X, r, ej);
-      else if (ej.cls == r.S) apply_death(X, r, ej);
-      else keep_going = apply_birth(X, r, ej);
+      if (ej.cls == r.S + 1) { apply_migration(X, r, ej); PROF_ADD(PH_MIGR); }
+      else if (ej.cls == r.S) { apply_death(X, r, ej); PROF_ADD(PH_DEATH); }
+      else { keep_going = apply_birth(X, r, ej); PROF_ADD(PH_BIRTH); }
     }
     if (!keep_going) break;
     if (do_bott) {
-      apply_excision(X, r, tb_fire, ratio_fire);
+      { Ctx<T> xc = X; Rep rc = r; apply_excision(xc, rc, tb_fire, ratio_fire); r = rc; }
+      PROF_ADD(PH_EXC);
       if (intent) r.bott_id = (r.bott_id < P.n_bott) ? r.bott_id + 1 : 0;
     }
     if (r.status == JSB_ST_INTERNAL) break;
   }
-  write_outputs(X, r);
+#ifdef JSB_PROFILE
+  if (lane == 0 && X.local_idx < 6) {
+    printf("rep %lld it %llu S %u n %u | refold %lld/%lld (elems %lld) draws %lld/%lld class %lld eval %lld time %lld | birth %lld/%lld death %lld/%lld migr %lld/%lld exc %lld\n",
+           (long long)X.local_idx, (unsigned long long)r.it, r.S, r.n, prof_c[PH_REFOLD], prof_n[PH_REFOLD], prof_fold,
+           prof_c[PH_DRAWS], prof_n[PH_DRAWS], prof_c[PH_CLASS], prof_c[PH_EVAL], prof_c[PH_TIME], prof_c[PH_BIRTH],
+           prof_n[PH_BIRTH], prof_c[PH_DEATH], prof_n[PH_DEATH], prof_c[PH_MIGR], prof_n[PH_MIGR], prof_c[PH_EXC]);
+  }
+#endif
+  { Ctx<T> xc = X; Rep rc = r; write_outputs(xc, rc); }
+}
+
+// Per-warp shared-memory slice:
+//   [ B: kSmemTable doubles | c_len: kTab u32 | c_off: kTab u32 | DevPoint | occupancy bits ]
+__host__ __device__ inline size_t smem_base_bytes() {
+  return sizeof(double) * kSmemTable + 2 * sizeof(uint32_t) * kTab + ((sizeof(DevPoint) + 15) & ~size_t(15));
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) ssa_kernel(const __grid_constant__ RunArgs A) {
-  __shared__ double s_tab[kWarpsPerBlock][kSmemTable + 32];
+__global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __grid_constant__ RunArgs A) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const uint64_t slot = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
+  const uint64_t slot = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   const WsLayout L = ws_layout(A.g.nv, A.arena_cap, (uint32_t)sizeof(T));
   uint8_t* base = A.ws + slot * A.ws_stride;
+  unsigned char* sw = s_dyn + (size_t)warp * A.smem_per_warp;
   Ctx<T> X;
   X.A = &A;
   X.lane = lane;
@@ -1355,20 +1541,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) ssa_kernel(const __gri
   X.arena = reinterpret_cast<T*>(base + L.arena);
   X.inds = reinterpret_cast<uint32_t*>(base + L.inds);
   X.samp = reinterpret_cast<uint32_t*>(base + L.samp);
-  X.c_off = reinterpret_cast<uint32_t*>(base + L.c_off);
-  X.c_len = reinterpret_cast<uint32_t*>(base + L.c_len);
   X.c_cap = reinterpret_cast<uint32_t*>(base + L.c_cap);
   X.c_alpha = reinterpret_cast<double*>(base + L.c_alpha);
   X.c_parent = reinterpret_cast<uint16_t*>(base + L.c_parent);
   X.c_label = reinterpret_cast<uint16_t*>(base + L.c_label);
-  X.g_B = reinterpret_cast<double*>(base + L.g_B);
   X.g_w = reinterpret_cast<double*>(base + L.g_w);
   X.g_c = reinterpret_cast<double*>(base + L.g_c);
-  X.s_B = s_tab[warp];
-  X.s_w = s_tab[warp] + kSmemTable;
-  X.B = X.s_B;
+  X.B = reinterpret_cast<double*>(sw);
+  X.c_len = reinterpret_cast<uint32_t*>(sw + sizeof(double) * kSmemTable);
+  X.c_off = X.c_len + kTab;
+  DevPoint* sP = reinterpret_cast<DevPoint*>(X.c_off + kTab);
+  X.occ = A.occ_words ? reinterpret_cast<uint32_t*>(sw + smem_base_bytes()) : nullptr;
   X.key.k0 = (uint32_t)A.seed;
   X.key.k1 = (uint32_t)(A.seed >> 32);
+  X.track_ids = (A.flags & (JSB_OUT_EVENTS | JSB_OUT_LATTICE)) != 0;
 
   for (;;) {
     unsigned long long idx = 0;
@@ -1378,7 +1564,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) ssa_kernel(const __gri
     const int64_t gidx = A.g_begin + (int64_t)idx;
     X.local_idx = (int64_t)idx;
     X.key.stream = (uint32_t)gidx;
-    const DevPoint* P = A.points + (gidx / A.reps_per_point);
+    {  // stage this replicate's sweep point in shared memory
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(A.points + (gidx / A.reps_per_point));
+      uint32_t* dst = reinterpret_cast<uint32_t*>(sP);
+      for (uint32_t i = lane; i < sizeof(DevPoint) / 4; i += 32) dst[i] = src[i];
+      __syncwarp();
+    }
+    const DevPoint* P = sP;
     X.P = P;
     X.tb = A.dpool + P->bott_off;
     X.ratio = X.tb + P->n_bott;
@@ -1390,21 +1582,42 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) ssa_kernel(const __gri
   }
 }
 
-int launch_ssa(const RunArgs& args, int grid_blocks, void* stream) {
+// Chooses the shared-memory layout (tables + occupancy bitmask when it fits) and the number of
+// warps per block (one block per SM).
+int ssa_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block) {
+  const uint32_t words = (args.g.nv + 31) / 32;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int max_optin = 0;
+  if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
+  const size_t with_occ = (smem_base_bytes() + 4ull * words + 15) & ~size_t(15);
+  const size_t without = (smem_base_bytes() + 15) & ~size_t(15);
+  int cap = kMaxWarpsPerBlock;
+  if (max_warps_per_sm > 0 && max_warps_per_sm < cap) cap = max_warps_per_sm;
+  int w_occ = (int)((size_t)max_optin / with_occ);
+  int w_no = (int)((size_t)max_optin / without);
+  if (w_occ > cap) w_occ = cap;
+  if (w_no > cap) w_no = cap;
+  // keep the bitmask unless it costs more than half of the resident warps
+  bool use_occ = w_occ >= 1 && w_occ * 2 >= w_no;
+  int w = use_occ ? w_occ : w_no;
+  if (w < 1) return -1;
+  args.occ_words = use_occ ? words : 0;
+  args.smem_per_warp = (uint32_t)(use_occ ? with_occ : without);
+  const int bytes = (int)((size_t)args.smem_per_warp * w);
+  if (cudaFuncSetAttribute(ssa_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(ssa_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+  *warps_per_block = w;
+  return 0;
+}
+
+int launch_ssa(const RunArgs& args, int grid_blocks, int warps_per_block, void* stream) {
+  const size_t smem = (size_t)args.smem_per_warp * warps_per_block;
   if (args.site_bytes == 2)
-    ssa_kernel<uint16_t><<<grid_blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(args);
+    ssa_kernel<uint16_t><<<grid_blocks, warps_per_block * 32, smem, (cudaStream_t)stream>>>(args);
   else
-    ssa_kernel<uint32_t><<<grid_blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(args);
+    ssa_kernel<uint32_t><<<grid_blocks, warps_per_block * 32, smem, (cudaStream_t)stream>>>(args);
   return (int)cudaGetLastError();
 }
-
-int ssa_max_blocks_per_sm() {
-  int a = 0, b = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, ssa_kernel<uint16_t>, kWarpsPerBlock * 32, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ssa_kernel<uint32_t>, kWarpsPerBlock * 32, 0);
-  return a < b ? a : b;
-}
-
-size_t ssa_smem_bytes() { return sizeof(double) * kWarpsPerBlock * (kSmemTable + 32); }
 
 }  // namespace jsb
