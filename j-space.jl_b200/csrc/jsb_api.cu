@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -25,6 +26,40 @@
 namespace {
 
 thread_local std::string g_err;
+
+// One pinned host staging buffer is kept between calls: pinning gigabytes costs seconds, the
+// event logs of an ensemble are that large, and callers typically run ensembles back to back.
+std::mutex g_pin_mu;
+void* g_pin_ptr = nullptr;
+size_t g_pin_bytes = 0;
+
+void* pinned_take(size_t bytes, size_t* got) {
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (g_pin_ptr && g_pin_bytes >= bytes) {
+      void* p = g_pin_ptr;
+      *got = g_pin_bytes;
+      g_pin_ptr = nullptr;
+      g_pin_bytes = 0;
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  *got = bytes;
+  return p;
+}
+
+void pinned_give(void* p, size_t bytes) {
+  if (!p) return;
+  void* drop = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (bytes > g_pin_bytes) { drop = g_pin_ptr; g_pin_ptr = p; g_pin_bytes = bytes; }
+    else drop = p;
+  }
+  if (drop) cudaFreeHost(drop);
+}
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -333,6 +368,7 @@ struct jsb_result {
   std::vector<long long> clone_off;
   std::vector<jsb_clone> clones;
   jsb_event* events = nullptr;  // pinned, replicate-major
+  size_t events_bytes = 0;
   std::vector<uint64_t> ev_off;  // n_local + 1
   std::vector<uint16_t> lat_clone;
   std::vector<uint32_t> lat_cell;
@@ -341,10 +377,10 @@ struct jsb_result {
   std::vector<int32_t> snap_count;
   double kernel_ms = 0.0;
   int64_t launches = 0;
-  ~jsb_result() {
-    if (events) cudaFreeHost(events);
-  }
+  ~jsb_result();
 };
+
+jsb_result::~jsb_result() { pinned_give(events, events_bytes); }
 
 namespace jsb {
 
@@ -667,7 +703,8 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
         gather_log_kernel<<<gblocks, 256, 0, stream>>>(d_log, d_chunk_owner, d_chunk_seq, d_ev_off, used_chunks, d_gather);
         CUDA_TRY(cudaGetLastError());
         res->launches += 1;
-        CUDA_TRY(cudaHostAlloc((void**)&res->events, sizeof(jsb_event) * total, cudaHostAllocDefault));
+        res->events = (jsb_event*)pinned_take(sizeof(jsb_event) * total, &res->events_bytes);
+        if (!res->events) { rc = fail(JSB_ENOMEM, "cannot pin %llu bytes of host memory for the event log", (unsigned long long)(sizeof(jsb_event) * total)); goto done; }
         CUDA_TRY(cudaMemcpyAsync(res->events, d_gather, sizeof(jsb_event) * total, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
       }
