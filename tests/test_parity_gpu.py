@@ -141,3 +141,88 @@ def test_clone_capacity_stop(jsb, oracle):
     p = dict(DEFAULT, rule="voter", Tf=150.0, mu_driver=0.1, rate_death=0.05)
     s = compare_runs(jsb, oracle, ("lattice", 2, 20, 20), p, reps=1)
     assert int(s[0]["status"]) == 2 and int(s[0]["n_clones"]) == 1000
+
+
+def test_gpu_matches_committed_golden_vectors(jsb, oracle):
+    # fixtures made by tests/golden/make_golden.py (CPU oracle); the GPU must reproduce the files
+    from golden.make_golden import CASES
+    from jspace_b200 import _lib as L
+    here = os.path.dirname(__file__)
+    for name, (spec, params, seed, stream) in CASES.items():
+        ref = np.load(os.path.join(here, "golden", f"{name}.npz"))
+        g = (jsb.Graph.lattice(spec[2], spec[3], spec[1]) if spec[0] == "lattice"
+             else jsb.Graph.dense_file(os.path.join(here, "golden", spec[1])))
+        res = jsb.run_ensemble(g, jsb.Point(**params), stream + 1, seed=seed, g_begin=stream, g_end=stream + 1,
+                               flags=L.OUT_EVENTS | L.OUT_LATTICE | L.OUT_LISTS)
+        assert res.summaries[0].tobytes() == ref["summary"][0].tobytes(), name
+        assert res.events(0).tobytes() == ref["events"].tobytes(), name
+        assert res.clones(0).tobytes() == ref["clones"].tobytes(), name
+        c, i = res.lattice(0)
+        assert np.array_equal(c, ref["clone_of_site"]) and np.array_equal(i, ref["cell_of_site"]), name
+        assert np.array_equal(res.list(0, 0), ref["cs_alive"]), name
+        res.close()
+
+
+def test_python_mirror_of_reference_api(jsb, oracle, tmp_path):
+    # simulate_evolution / Start_J_Space keep the reference's signatures and 7-tuple
+    G = jsb.spatial_graph(30, 30, jsb.PhiloxSeed(1234), dim=2, n_cell=1)
+    seed = jsb.PhiloxSeed(1234)
+    df, G2, n_alive, set_mut, gs, ca, alpha = jsb.simulate_evolution(
+        G, 60.0, 0.2, 0.01, 0.01, 0.05, 0.4, 0.1, "contact", seed, Time_of_sampling=[10, 20],
+        t_bottleneck=[30.0], ratio_bottleneck=[0.5])
+    o = oracle.Run(oracle.Graph.lattice(2, 30, 30), oracle.make_params(
+        Tf=60.0, mu_driver=0.05, t_bottleneck=[30.0], ratio_bottleneck=[0.5], t_snapshot=[10.0, 20.0]), 1234, 0,
+        faithful=False)
+    assert df.records.tobytes() == o.events.tobytes()
+    assert n_alive == o.series.tolist() and alpha == o.clones["alpha"].tolist()
+    assert set_mut[0] == 1 and all(g[0] == 1 for g in set_mut[1:]) and len(gs) == 2
+    assert sorted(G2.cells_alive()) == sorted(o.lists[0].tolist())
+    assert len(gs[1].cells_alive()) == int(o.snapshots["n_alive"][1])
+    v = G2.cells_alive()[0]
+    assert G2.get_prop(v, "Fit") == alpha[G2.get_prop(v, "Subpop") - 1]
+    # the next call on the same seed object uses the next stream, like a shared MersenneTwister
+    df2 = jsb.simulate_evolution(G, 30.0, 0.2, 0.01, 0.01, 0.05, 0.4, 0.1, "contact", seed)[0]
+    o2 = oracle.Run(oracle.Graph.lattice(2, 30, 30), oracle.make_params(Tf=30.0, mu_driver=0.05), 1234, 1, faithful=False)
+    assert df2.records.tobytes() == o2.events.tobytes()
+    # Start_J_Space: same TOML keys as the reference's Parameters.toml / Config.toml
+    (tmp_path / "P.toml").write_text(
+        '[[Graph]]\nrow = 20\ncol = 20\ndim = 2\nN_starting_cells = 1\n[[Dynamic]]\nModel = "contact"\nMax_time = 50.0\n'
+        'rate_birth = 0.2\nrate_death = 0.01\nrate_migration = 0.01\ndrive_mut_rate = 0.01\n'
+        'average_driver_mut_rate = 0.4\nstd_driver_mut_rate = 0.1\nt_bottleneck = [25.0]\nratio_bottleneck = [0.5]\n')
+    (tmp_path / "C.toml").write_text(
+        f'[[Config]]\nseed = 1234\npath_to_save_files = "{tmp_path}/out/"\nGenerate_graph = 1\n'
+        'Path_to_Graph = ""\nTree_Driver_Configure = 0\nedgelist_treedriver = ""\ndriver_birth_rates = ""\n'
+        '[[OutputGT]]\nDriver_list = 1\n[[FileOutputPlot]]\nTime_of_sampling = [10, 20]\nGraph_configuration = 1\n')
+    out = jsb.Start_J_Space(str(tmp_path / "P.toml"), str(tmp_path / "C.toml"))
+    files = sorted(os.listdir(tmp_path / "out"))
+    assert files == ["CA_subpop.csv", "Dinamica.csv", "DriverList.csv", "n_cell_alive.csv"]
+    assert (tmp_path / "out" / "DriverList.csv").read_text().splitlines()[0] == "1,0.2"
+    assert len((tmp_path / "out" / "n_cell_alive.csv").read_text().splitlines()) == len(out[2])
+    assert (tmp_path / "out" / "Dinamica.csv").read_text().splitlines()[0] == "Event,Time,Cell,Notes"
+
+
+def test_genealogy_of_sampled_cells(jsb, oracle):
+    # jsb_result_genealogy == create_matrix_relational (reference :60-104) restated on the oracle's log
+    from jspace_b200 import _lib as L
+    g = jsb.Graph.lattice(30, 30, 2)
+    p = dict(DEFAULT, Tf=60.0, mu_driver=0.05)
+    res = jsb.run_ensemble(g, jsb.Point(**p), 1, seed=5, flags=L.OUT_EVENTS | L.OUT_LATTICE)
+    ev, (clone, cid), clones = res.events(0), res.lattice(0), res.clones(0)
+    alive = cid[cid > 0]
+    rng = np.random.default_rng(0)
+    sample = rng.choice(alive, size=min(10, len(alive)), replace=False).astype(np.uint32)
+    rel = res.genealogy(0, sample)
+    # restatement of the backward scan
+    wanted = set(int(x) for x in sample)
+    rows = []
+    for e in ev[::-1]:
+        if e["type"] not in (L.EV_DUPLICATE, L.EV_MUTATION) or int(e["cell"]) not in wanted:
+            continue
+        wanted.discard(int(e["cell"]))
+        wanted.add(int(e["parent"]))
+        sub = int(clones["parent"][e["clone"] - 1]) if e["type"] == L.EV_MUTATION else int(e["clone"])
+        rows.append((int(e["parent"]), int(e["cell"]), float(e["time"]), sub, int(e["type"])))
+    got = [(int(r["father"]), int(r["child"]), float(r["time"]), int(r["subpop_child"]), int(r["type"])) for r in rel]
+    assert got == rows and len(rows) >= len(sample)
+    assert wanted == {1}  # every sampled lineage coalesces in the seed cell
+    res.close()
