@@ -645,7 +645,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     a.points = d_points; a.dpool = d_dpool; a.ipool = d_ipool;
     a.seed_cand = g->d_cand; a.n_cand = g->d_ncand;
     a.flags = opts->flags; a.seed = opts->seed; a.g_begin = g_begin; a.n_local = n_local; a.reps_per_point = reps_per_point;
-    a.ws = d_ws; a.ws_stride = L.total; a.arena_cap = arena_cap; a.site_bytes = site_bytes;
+    a.ws = d_ws; a.ws_stride = L.total; a.arena_cap = arena_cap; a.site_bytes = site_bytes; a.L = L;
     a.summaries = d_sum; a.clone_pool = d_clones; a.clone_pool_cap = clone_cap; a.clone_pool_next = d_counters + 1;
     a.clone_off = d_clone_off;
     a.log_pool = d_log; a.n_chunks = n_chunks; a.chunk_next = d_chunk_next; a.chunk_owner = d_chunk_owner; a.chunk_seq = d_chunk_seq;

@@ -8,7 +8,7 @@ namespace jsb {
 
 constexpr int kMaxClones = 1000;   // Set(1:1000), src/J_Space.jl:366
 constexpr int kTab = 1024;         // clone-table stride
-constexpr int kSmemTable = 1008;   // class boundaries (S+2 <= 1002) in the per-warp smem slice
+constexpr int kSmemTable = 1024;   // class boundaries (S+2 <= 1002), padded with +inf, per-warp smem slice
 constexpr double kGuardEps = 1e-11; // class-selection guard band (relative to λ), DESIGN.md §4
 constexpr int kLogChunk = 1024;    // records per event-log chunk (32 KB)
 constexpr int kMinListCap = 32;    // initial capacity of a ca_subpop list in the arena
@@ -50,6 +50,11 @@ struct DevPoint {
   int32_t pad;
 };
 
+// Workspace layout per slot (all offsets 16-byte aligned); computed identically on host and device.
+struct WsLayout {
+  uint64_t clone, cellid, A, arena, inds, samp, c_off, c_len, c_cap, c_alpha, c_parent, c_label, g_B, g_w, g_c,
+      total;
+};
 struct RunArgs {
   DevGraph g;
   const DevPoint* points;
@@ -69,6 +74,7 @@ struct RunArgs {
   uint32_t site_bytes; // 2 when nv <= 65536, else 4 (storage type of the ordered lists)
   uint32_t occ_words;  // per-warp shared occupancy bitmask words (0 = lattice too large, use global)
   uint32_t smem_per_warp;  // bytes of dynamic shared memory per warp
+  WsLayout L;          // workspace offsets (computed once on the host)
   // outputs
   jsb_summary* summaries;
   jsb_clone* clone_pool;
@@ -88,11 +94,6 @@ struct RunArgs {
   unsigned long long* work_counter;
 };
 
-// Workspace layout per slot (all offsets 16-byte aligned); computed identically on host and device.
-struct WsLayout {
-  uint64_t clone, cellid, A, arena, inds, samp, c_off, c_len, c_cap, c_alpha, c_parent, c_label, g_B, g_w, g_c,
-      total;
-};
 __host__ __device__ inline uint64_t jsb_align16(uint64_t x) { return (x + 15) & ~uint64_t(15); }
 __host__ __device__ inline WsLayout ws_layout(uint32_t nv, uint32_t arena_cap, uint32_t site_bytes) {
   WsLayout L;

@@ -141,6 +141,28 @@ __device__ __forceinline__ double contract_log(double x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Explicit shared-memory accesses for the hot reads.  The per-warp slices are addressed by 32-bit
+// shared-window offsets kept in registers; going through generic pointers made ptxas re-derive the
+// window base (S2UR SR_CgaCtaId + LDC + IMAD) in front of every access.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Graph access (0-based vertices on the device; the ABI adds 1)
 // ---------------------------------------------------------------------------------------------
 // Implicit lattice of Graphs.grid((n1,n2,n3)): vertex = x + y*n1 + z*n1*n2, neighbours ascending:
@@ -189,6 +211,8 @@ struct Ctx {
   double *g_w, *g_c;        // global-memory scratch of the exact prob_cum fallback
   double* B;                // per-warp shared slice: class boundaries [kSmemTable]
   uint32_t* occ;            // per-warp shared occupancy bitmask (nullptr: test clone[] in global)
+  uint32_t sB, sLen, sOff, sOcc;  // the same slices as 32-bit shared-window addresses (sOcc = 0: none)
+  uint32_t search_top;      // power of two >= S+2: first probe distance of the class search
   Key key;
   int64_t local_idx;
   int lane;
@@ -605,6 +629,11 @@ __device__ __forceinline__ void refold(Ctx<T>& X, Rep& r) {
     B[S] = bd;
     B[S + 1] = lambda;
   }
+  {
+    uint32_t top = X.search_top;
+    while (top < S + 2) top <<= 1;
+    X.search_top = top;
+  }
   r.lambda = lambda;
   r.theta = 1.0 / lambda;                                 // Exponential(1 / λ) :699
   r.guard = ((X.P->quirks & JSB_QUIRK_DEBUG_WIDE_GUARD) ? 1e-3 : kGuardEps) * lambda;
@@ -673,13 +702,25 @@ struct Eval {
   bool effective;
 };
 
-// first i in [0, n) with !(tab[i] < key); n when none.  All values are non-negative doubles, so
-// the IEEE bit patterns order like the numbers and the search runs on integer compares (an fp64
-// compare costs a full ~32-cycle fp64 pipe round trip on this part); fixed 10 steps, no branches.
+// Class search: first i with !(B[i] < key).  The table is padded with +inf up to kSmemTable, all
+// values are non-negative doubles, so the IEEE bit patterns order like the numbers and the search
+// is a branch-free sequence of integer compares on ld.shared (an fp64 compare costs a full fp64
+// pipe round trip on this part).  `top` = power of two >= S+2.
+__device__ __forceinline__ uint32_t class_search(uint32_t sB, uint32_t top, double key) {
+  const unsigned long long k = (unsigned long long)__double_as_longlong(key);
+  uint32_t lo = 0;  // number of leading entries known to be < key
+  for (uint32_t step = top; step > 0; step >>= 1) {
+    const unsigned long long v = lds_u64(sB + (lo + step - 1u) * 8u);
+    lo = v < k ? lo + step : lo;
+  }
+  return lo;
+}
+
+// same search on a global-memory table of n entries (exact prob_cum fallback; rare)
 __device__ __forceinline__ uint32_t lower_bound(const double* tab, uint32_t n, double key) {
   const unsigned long long* t = reinterpret_cast<const unsigned long long*>(tab);
   const unsigned long long k = (unsigned long long)__double_as_longlong(key);
-  uint32_t lo = 0;  // number of leading entries known to be < key
+  uint32_t lo = 0;
 #pragma unroll
   for (uint32_t step = 512; step > 0; step >>= 1) {
     uint32_t probe = lo + step;
@@ -696,7 +737,7 @@ __device__ __forceinline__ void eval_member(const Ctx<T>& X, const Rep& r, uint6
   const uint32_t S = r.S;
   const bool is_birth = cls < S;
   const uint32_t ci = is_birth ? cls : 0u;
-  const uint32_t off = X.c_off[ci], cl = X.c_len[ci];
+  const uint32_t off = lds_u32(X.sOff + ci * 4u), cl = lds_u32(X.sLen + ci * 4u);
   const T* list = is_birth ? X.arena + off : X.Alist;
   const uint32_t llen = is_birth ? cl : r.n;
   // cls >= S+2: findfirst -> nothing in the reference; llen == 0: rand(1:0) throws.  Contract:
@@ -731,7 +772,7 @@ __device__ __forceinline__ bool eval_target(const Ctx<T>& X, const Rep& r, uint6
   if (X.occ) {
     // `pos ∈ cs_alive` from the shared bitmask; the clone id itself is only needed when a voter
     // rule may displace the occupant
-    const bool occupied = (X.occ[pos >> 5] >> (pos & 31)) & 1u;
+    const bool occupied = (lds_u32(X.sOcc + (pos >> 5) * 4u) >> (pos & 31)) & 1u;
     occ = occupied ? ((model == JSB_RULE_CONTACT || cls == S + 1) ? 1u : (uint32_t)X.clone[pos]) : 0u;
   } else {
     occ = X.clone[pos];
@@ -769,9 +810,10 @@ __device__ __forceinline__ void batch_eval(Ctx<T>& X, Rep& r, bool force_exact, 
     dtv[u] = (-contract_log(u01_open(wa))) * r.theta;  // :699
     // event class: k·λ against the folded boundaries
     const double key = u01_53(wb) * r.lambda;          // :721
-    const uint32_t c = lower_bound(X.B, nb, key);
+    const uint32_t c = class_search(X.sB, X.search_top, key);
     const uint32_t cc = c < nb ? c : nb - 1;
-    unc[u] = force_exact || c >= nb || (X.B[cc] - key <= r.guard) || (cc > 0 && key - X.B[cc - 1] <= r.guard);
+    const double hi_b = lds_f64(X.sB + cc * 8u), lo_b = lds_f64(X.sB + (cc > 0 ? cc - 1 : 0) * 8u);
+    unc[u] = force_exact || c >= nb || (hi_b - key <= r.guard) || (cc > 0 && key - lo_b <= r.guard);
     unc_any = unc_any || unc[u];
     cls[u] = c;
   }
@@ -1157,6 +1199,7 @@ __device__ __noinline__ void seed_replicate(Ctx<T>& X, Rep& r) {
   for (uint32_t i = lane; i < (g.nv + 1) / 2; i += 32) reinterpret_cast<uint32_t*>(X.clone)[i] = 0;
   if (X.occ)
     for (uint32_t i = lane; i < X.A->occ_words; i += 32) X.occ[i] = 0;
+  for (uint32_t i = lane; i < (uint32_t)kSmemTable; i += 32) X.B[i] = __longlong_as_double(0x7ff0000000000000ll);  // +inf pad
   __syncwarp();
   uint32_t n0 = 0;
   if (P.n_start == 1) {
@@ -1367,6 +1410,7 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X) {
   r.log_on = (A.flags & JSB_OUT_EVENTS) != 0;
   r.exact_valid = false;
   r.dirty_from = 0;
+  X.search_top = 2;
   { Ctx<T> xc = X; Rep rc = r; seed_replicate(xc, rc); r = rc; }
 
   const bool intent = (P.quirks & JSB_QUIRK_EXCISION_INTENT) != 0;
@@ -1529,7 +1573,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint64_t slot = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  const WsLayout L = ws_layout(A.g.nv, A.arena_cap, (uint32_t)sizeof(T));
+  const WsLayout& L = A.L;
   uint8_t* base = A.ws + slot * A.ws_stride;
   unsigned char* sw = s_dyn + (size_t)warp * A.smem_per_warp;
   Ctx<T> X;
@@ -1552,6 +1596,11 @@ __global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __
   X.c_off = X.c_len + kTab;
   DevPoint* sP = reinterpret_cast<DevPoint*>(X.c_off + kTab);
   X.occ = A.occ_words ? reinterpret_cast<uint32_t*>(sw + smem_base_bytes()) : nullptr;
+  X.sB = smem_addr(X.B);
+  X.sLen = smem_addr(X.c_len);
+  X.sOff = smem_addr(X.c_off);
+  X.sOcc = X.occ ? smem_addr(X.occ) : 0u;
+  X.search_top = 2;
   X.key.k0 = (uint32_t)A.seed;
   X.key.k1 = (uint32_t)(A.seed >> 32);
   X.track_ids = (A.flags & (JSB_OUT_EVENTS | JSB_OUT_LATTICE)) != 0;
