@@ -521,6 +521,8 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
   jsb_snapshot* d_snaps = nullptr;
   uint16_t* d_out_clone = nullptr;
   uint32_t *d_out_cell = nullptr, *d_out_lists = nullptr;
+  uint32_t* d_order = nullptr;
+  float* d_prio = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t stream = nullptr;
   int prev_dev = 0;
@@ -656,11 +658,38 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
     CUDA_TRY(cudaEventRecord(ev0, stream));
+    // Optional longest-first scheduling (JSB_PILOT=1): a short pilot pass (8192 iterations per
+    // replicate; its work estimate has rank correlation ~0.97 with the final iteration counts)
+    // orders the full pass longest first.  Off by default: on the C2 ensemble the kernel time is
+    // the latency of the single heaviest replicate (measured: 2.82 s with, 2.76 s without).
+    if ((uint64_t)n_local > slots && (uint64_t)n_local <= 16 * slots && std::getenv("JSB_PILOT")) {
+      CUDA_TRY(cudaMalloc(&d_prio, sizeof(float) * n_local));
+      CUDA_TRY(cudaMalloc(&d_order, sizeof(uint32_t) * n_local));
+      RunArgs pa = a;
+      pa.pilot_iters = 8192;
+      pa.prio = d_prio;
+      pa.flags = 0;
+      pa.clone_pool = nullptr;
+      pa.out_clone = nullptr; pa.out_cell = nullptr; pa.out_lists = nullptr; pa.snaps = nullptr;
+      int prc = launch_ssa(pa, grid, wpb, stream);
+      if (prc != 0) { rc = fail(JSB_ECUDA, "pilot launch failed: %s", cudaGetErrorString((cudaError_t)prc)); goto done; }
+      res->launches += 1;
+      std::vector<float> prio((size_t)n_local);
+      CUDA_TRY(cudaMemcpyAsync(prio.data(), d_prio, sizeof(float) * n_local, cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      std::vector<uint32_t> order((size_t)n_local);
+      for (int64_t i = 0; i < n_local; ++i) order[i] = (uint32_t)i;
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return prio[x] > prio[y]; });
+      CUDA_TRY(cudaMemcpyAsync(d_order, order.data(), sizeof(uint32_t) * n_local, cudaMemcpyHostToDevice, stream));
+      CUDA_TRY(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long), stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));  // `order` is a host temporary
+      a.order = d_order;
+    }
     {
       int lrc = launch_ssa(a, grid, wpb, stream);
       if (lrc != 0) { rc = fail(JSB_ECUDA, "kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc)); goto done; }
     }
-    res->launches = 1;
+    res->launches += 1;
     CUDA_TRY(cudaEventRecord(ev1, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     {
@@ -735,7 +764,7 @@ done:
   cudaFree(d_points); cudaFree(d_dpool); cudaFree(d_ipool); cudaFree(d_ws); cudaFree(d_sum); cudaFree(d_clones);
   cudaFree(d_counters); cudaFree(d_clone_off); cudaFree(d_log); cudaFree(d_gather); cudaFree(d_chunk_next);
   cudaFree(d_chunk_owner); cudaFree(d_chunk_seq); cudaFree(d_ev_off); cudaFree(d_snaps); cudaFree(d_out_clone);
-  cudaFree(d_out_cell); cudaFree(d_out_lists);
+  cudaFree(d_out_cell); cudaFree(d_out_lists); cudaFree(d_order); cudaFree(d_prio);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (stream) cudaStreamDestroy(stream);

@@ -92,6 +92,11 @@ struct RunArgs {
   uint32_t* out_cell;
   uint32_t* out_lists;  // [n_local][2][nv]: cs_alive then concatenated ca_subpop
   unsigned long long* work_counter;
+  // longest-first scheduling: a pilot pass runs every replicate for `pilot_iters`
+  // iterations and writes a work estimate; the full pass then takes replicates in `order`
+  const uint32_t* order;  // nullptr: natural order
+  uint64_t pilot_iters;   // > 0: pilot pass (no outputs except prio)
+  float* prio;
 };
 
 __host__ __device__ inline uint64_t jsb_align16(uint64_t x) { return (x + 15) & ~uint64_t(15); }

@@ -1407,7 +1407,7 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X) {
   r.snap_idx = 0;
   r.status = JSB_ST_OK;
   r.n_eff = r.n_births = r.n_deaths = r.n_migr = r.n_disp = r.n_exc = 0;
-  r.log_on = (A.flags & JSB_OUT_EVENTS) != 0;
+  r.log_on = (A.flags & JSB_OUT_EVENTS) != 0 && A.pilot_iters == 0;
   r.exact_valid = false;
   r.dirty_from = 0;
   X.search_top = 2;
@@ -1558,6 +1558,11 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X) {
            prof_n[PH_BIRTH], prof_c[PH_DEATH], prof_n[PH_DEATH], prof_c[PH_MIGR], prof_n[PH_MIGR], prof_c[PH_EXC]);
   }
 #endif
+  if (A.pilot_iters) {
+    // work estimate for longest-first scheduling: iterations left if the total rate stayed as it is
+    if (lane == 0) A.prio[X.local_idx] = (r.n > 0 && r.t < P.Tf) ? (float)(r.lambda * (P.Tf - r.t)) : 0.0f;
+    return;
+  }
   { Ctx<T> xc = X; Rep rc = r; write_outputs(xc, rc); }
 }
 
@@ -1610,6 +1615,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __
     if (lane == 0) idx = atomicAdd(A.work_counter, 1ull);
     idx = __shfl_sync(FULL, idx, 0);
     if ((long long)idx >= A.n_local) break;
+    if (A.order) idx = A.order[idx];
     const int64_t gidx = A.g_begin + (int64_t)idx;
     X.local_idx = (int64_t)idx;
     X.key.stream = (uint32_t)gidx;
@@ -1617,6 +1623,8 @@ __global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __
       const uint32_t* src = reinterpret_cast<const uint32_t*>(A.points + (gidx / A.reps_per_point));
       uint32_t* dst = reinterpret_cast<uint32_t*>(sP);
       for (uint32_t i = lane; i < sizeof(DevPoint) / 4; i += 32) dst[i] = src[i];
+      __syncwarp();
+      if (A.pilot_iters && lane == 0 && (sP->max_iter == 0 || sP->max_iter > A.pilot_iters)) sP->max_iter = A.pilot_iters;
       __syncwarp();
     }
     const DevPoint* P = sP;
