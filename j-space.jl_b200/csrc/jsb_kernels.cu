@@ -88,6 +88,13 @@ __device__ __forceinline__ void draw_block(const Key& key, uint64_t iter, uint32
   b = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
 }
 
+// Out-of-line copy for everything outside the speculative window (code size: the inlined Philox is
+// ~120 instructions per call site and the kernel is instruction-fetch sensitive).
+__device__ __noinline__ void draw_block_nl(Key key, uint64_t iter, uint32_t attempt, uint32_t site, uint32_t seq,
+                                           uint64_t& a, uint64_t& b) {
+  draw_block(key, iter, attempt, site, seq, a, b);
+}
+
 // Rejection branch of Lemire's bounded draw (probability s / 2^64 per draw): out of line.
 __device__ __noinline__ uint32_t bounded_retry(Key key, uint64_t lo, uint64_t hi, uint32_t s, uint64_t iter,
                                                uint32_t site, uint32_t seq, int half) {
@@ -96,7 +103,7 @@ __device__ __noinline__ uint32_t bounded_retry(Key key, uint64_t lo, uint64_t hi
   while (lo < t) {
     ++attempt;
     uint64_t a, b;
-    draw_block(key, iter, attempt, site, seq, a, b);
+    draw_block_nl(key, iter, attempt, site, seq, a, b);
     uint64_t w = half ? b : a;
     hi = __umul64hi(w, (uint64_t)s);
     lo = w * (uint64_t)s;
@@ -278,17 +285,41 @@ __device__ __forceinline__ void log_store(jsb_event* dst, int half, double time,
   reinterpret_cast<uint4*>(dst)[half] = v;
 }
 
+// Out-of-line row writer (only reached when the log is requested); returns the chunk in use or
+// kNone when the pool is exhausted.
+__device__ __noinline__ uint32_t log_emit(const RunArgs* A, int64_t local_idx, int lane, uint64_t nlog, uint32_t cur_chunk,
+                                          uint32_t type, uint32_t flags, double time, uint32_t cell, uint32_t parent,
+                                          uint32_t site1, uint32_t site2, uint32_t clone, uint32_t label) {
+  const uint32_t slot = (uint32_t)(nlog % kLogChunk);
+  if (slot == 0) {
+    uint32_t c = 0;
+    if (lane == 0) {
+      c = atomicAdd(A->chunk_next, 1u);
+      if (c < A->n_chunks) {
+        A->chunk_owner[c] = (int32_t)local_idx;
+        A->chunk_seq[c] = (uint32_t)(nlog / kLogChunk);
+      }
+    }
+    c = __shfl_sync(FULL, c, 0);
+    if (c >= A->n_chunks) return kNone;
+    cur_chunk = c;
+  }
+  if (lane < 2) {
+    jsb_event* dst = A->log_pool + (size_t)cur_chunk * kLogChunk + slot;
+    log_store(dst, lane, time, cell, parent, site1, site2, clone, label, type, flags);
+  }
+  return cur_chunk;
+}
+
 template <typename T>
 __device__ __forceinline__ void log_row(Ctx<T>& X, Rep& r, uint32_t type, uint32_t flags, double time, uint32_t cell,
                                         uint32_t parent, uint32_t site0, uint32_t site2_1, uint32_t clone,
                                         uint32_t label) {
   if (r.log_on) {
-    uint32_t slot = (uint32_t)(r.nlog % kLogChunk);
-    if (slot == 0) { Ctx<T> xc = X; Rep rc = r; log_open_chunk(xc, rc); r = rc; }
-    if (r.log_on && X.lane < 2) {
-      jsb_event* dst = X.A->log_pool + (size_t)r.cur_chunk * kLogChunk + slot;
-      log_store(dst, X.lane, time, cell, parent, site0 + 1, site2_1, clone, label, type, flags);
-    }
+    const uint32_t c = log_emit(X.A, X.local_idx, X.lane, r.nlog, r.cur_chunk, type, flags, time, cell, parent,
+                                site0 + 1, site2_1, clone, label);
+    if (c == kNone) { r.log_on = false; r.status = JSB_ST_LOG_OVERFLOW; }
+    else r.cur_chunk = c;
   }
   r.nlog++;
 }
@@ -923,7 +954,7 @@ __device__ __noinline__ uint32_t pick_label(uint32_t used_w, uint32_t j, int lan
 __device__ __noinline__ double contract_randn(Key key, uint64_t iter) {
   for (uint32_t attempt = 0;; ++attempt) {
     uint64_t a, b;
-    draw_block(key, iter, 0, DS_NORMAL, attempt, a, b);
+    draw_block_nl(key, iter, 0, DS_NORMAL, attempt, a, b);
     double v1 = 2.0 * u01_53(a) - 1.0;
     double v2 = 2.0 * u01_53(b) - 1.0;
     double s = v1 * v1 + v2 * v2;
@@ -958,7 +989,7 @@ __device__ __forceinline__ bool apply_birth(Ctx<T>& X, Rep& r, const Eval& e) {
   const DevPoint& P = *X.P;
   const uint32_t sp = e.cls + 1;  // :Subpop of the dividing cell (== min)
   uint64_t wa, wb;
-  draw_block(X.key, r.it, 0, DS_DRIVER_COIN, 0, wa, wb);
+  draw_block_nl(X.key, r.it, 0, DS_DRIVER_COIN, 0, wa, wb);
   const double rr = u01_53(wa);  // :347 / :447
   int child_node = -1;
   bool driver;
@@ -1005,7 +1036,7 @@ __device__ __forceinline__ bool apply_birth(Ctx<T>& X, Rep& r, const Eval& e) {
     } else {
       uint32_t n_free = 1000u - r.S;  // one label per clone, the founder holds label 1
       uint64_t a, b;
-      draw_block(X.key, r.it, 0, DS_LABEL, 0, a, b);
+      draw_block_nl(X.key, r.it, 0, DS_LABEL, 0, a, b);
       uint32_t j = bounded(X.key, a, n_free, r.it, DS_LABEL, 0, 0);  // :371
       label = pick_label(r.used_w, j, X.lane);
       if ((uint32_t)X.lane == (label >> 5)) r.used_w |= 1u << (label & 31u);
@@ -1061,14 +1092,14 @@ __device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double
   const int lane = X.lane;
   if (k == 1) {
     uint64_t a, b;
-    draw_block(X.key, r.it, 0, DS_EXCISION, 0, a, b);
+    draw_block_nl(X.key, r.it, 0, DS_EXCISION, 0, a, b);
     uint32_t i = bounded(X.key, a, n, r.it, DS_EXCISION, 0, 0);
     if (lane == 0) samp[0] = (uint32_t)X.Alist[i];
   } else if (k == 2) {  // samplepair
     uint64_t a, b;
-    draw_block(X.key, r.it, 0, DS_EXCISION, 0, a, b);
+    draw_block_nl(X.key, r.it, 0, DS_EXCISION, 0, a, b);
     uint32_t i1 = bounded(X.key, a, n, r.it, DS_EXCISION, 0, 0) + 1;
-    draw_block(X.key, r.it, 0, DS_EXCISION, 1, a, b);
+    draw_block_nl(X.key, r.it, 0, DS_EXCISION, 1, a, b);
     uint32_t i2 = bounded(X.key, a, n - 1, r.it, DS_EXCISION, 1, 0) + 1;
     if (lane == 0) {
       samp[0] = (uint32_t)X.Alist[i1 - 1];
@@ -1082,7 +1113,7 @@ __device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double
       uint32_t jmine = 0;
       if (i < k) {
         uint64_t a, b;
-        draw_block(X.key, r.it, 0, DS_EXCISION, i, a, b);
+        draw_block_nl(X.key, r.it, 0, DS_EXCISION, i, a, b);
         jmine = i + bounded(X.key, a, n - i, r.it, DS_EXCISION, i, 0);  // rand(i:n)
       }
       uint32_t cnt = (k - base) < 32u ? (k - base) : 32u;
@@ -1107,7 +1138,7 @@ __device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double
         uint32_t idx;
         for (;;) {
           uint64_t a, b;
-          draw_block(X.key, r.it, 0, DS_EXCISION, q, a, b);
+          draw_block_nl(X.key, r.it, 0, DS_EXCISION, q, a, b);
           idx = bounded(X.key, a, n, r.it, DS_EXCISION, q, 0);
           ++q;
           if (!inds[idx]) break;
@@ -1207,7 +1238,7 @@ __device__ __noinline__ void seed_replicate(Ctx<T>& X, Rep& r) {
       uint32_t j = 0;
       if (X.A->n_cand > 1) {
         uint64_t a, b;
-        draw_block(X.key, 0, 0, DS_SEED_TIE, 0, a, b);
+        draw_block_nl(X.key, 0, 0, DS_SEED_TIE, 0, a, b);
         j = bounded(X.key, a, X.A->n_cand, 0, DS_SEED_TIE, 0, 0);  // :86
       }
       uint32_t v0 = X.A->seed_cand[j];
@@ -1226,7 +1257,7 @@ __device__ __noinline__ void seed_replicate(Ctx<T>& X, Rep& r) {
       uint32_t cnt = 0;
       for (int i = 0; i < P.n_start; ++i) {
         uint64_t a, b;
-        draw_block(X.key, 0, 0, DS_SEED_POS, (uint32_t)i, a, b);
+        draw_block_nl(X.key, 0, 0, DS_SEED_POS, (uint32_t)i, a, b);
         uint32_t pos = bounded(X.key, a, g.nv - (uint32_t)i, 0, DS_SEED_POS, (uint32_t)i, 0);  // 0-based rank
         uint32_t ins = 0;
         for (uint32_t q = 0; q < cnt; ++q)
