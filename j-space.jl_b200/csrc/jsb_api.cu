@@ -13,6 +13,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -33,6 +34,19 @@ std::mutex g_pin_mu;
 void* g_pin_ptr = nullptr;
 size_t g_pin_bytes = 0;
 
+// JSB_TIMING=1: phase timings of jsb_run on stderr
+struct PhaseTimer {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  PhaseTimer() : on(std::getenv("JSB_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[jsb_run] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 void* pinned_take(size_t bytes, size_t* got) {
   {
     std::lock_guard<std::mutex> lk(g_pin_mu);
@@ -44,9 +58,17 @@ void* pinned_take(size_t bytes, size_t* got) {
       return p;
     }
   }
+  // ensembles run back to back produce logs of similar but not equal size: leave headroom so the
+  // cached buffer fits the next call (pinning gigabytes takes seconds)
+  size_t want = bytes + bytes / 4;
+  want = (want + (size_t(256) << 20) - 1) & ~((size_t(256) << 20) - 1);
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-  *got = bytes;
+  if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  }
+  *got = want;
   return p;
 }
 
@@ -367,12 +389,14 @@ struct jsb_result {
   std::vector<jsb_summary> summaries;
   std::vector<long long> clone_off;
   std::vector<jsb_clone> clones;
-  jsb_event* events = nullptr;  // pinned, replicate-major
-  size_t events_bytes = 0;
+  // one pinned host block (cached between calls): [events | lattice clone | lattice cell | lists]
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  jsb_event* events = nullptr;  // replicate-major
   std::vector<uint64_t> ev_off;  // n_local + 1
-  std::vector<uint16_t> lat_clone;
-  std::vector<uint32_t> lat_cell;
-  std::vector<uint32_t> lists;
+  uint16_t* lat_clone = nullptr;
+  uint32_t* lat_cell = nullptr;
+  uint32_t* lists = nullptr;
   std::vector<jsb_snapshot> snaps;
   std::vector<int32_t> snap_count;
   double kernel_ms = 0.0;
@@ -380,7 +404,7 @@ struct jsb_result {
   ~jsb_result();
 };
 
-jsb_result::~jsb_result() { pinned_give(events, events_bytes); }
+jsb_result::~jsb_result() { pinned_give(pinned, pinned_bytes); }
 
 namespace jsb {
 
@@ -495,6 +519,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
 
   const int64_t n_local = g_end - g_begin;
   int rc = JSB_OK;
+  PhaseTimer pt;
   jsb_result* res = new (std::nothrow) jsb_result();
   if (!res) return fail(JSB_ENOMEM, "out of host memory");
   res->n_local = n_local;
@@ -518,6 +543,8 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
   int32_t* d_chunk_owner = nullptr;
   uint32_t* d_chunk_seq = nullptr;
   unsigned long long* d_ev_off = nullptr;
+  uint64_t ev_total = 0;
+  uint32_t ev_used_chunks = 0;
   jsb_snapshot* d_snaps = nullptr;
   uint16_t* d_out_clone = nullptr;
   uint32_t *d_out_cell = nullptr, *d_out_lists = nullptr;
@@ -655,6 +682,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     a.out_clone = d_out_clone; a.out_cell = d_out_cell; a.out_lists = d_out_lists;
     a.work_counter = d_counters;
 
+    pt.mark("setup + allocations");
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
     CUDA_TRY(cudaEventRecord(ev0, stream));
@@ -698,6 +726,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
       res->kernel_ms = ms;
     }
 
+    pt.mark("simulation kernel");
     // ---- copy back ------------------------------------------------------------------------
     res->summaries.resize((size_t)n_local);
     CUDA_TRY(cudaMemcpy(res->summaries.data(), d_sum, sizeof(jsb_summary) * n_local, cudaMemcpyDeviceToHost));
@@ -723,21 +752,45 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
         uint64_t logged = std::min<uint64_t>(res->summaries[i].n_events, (uint64_t)chunks_of[i] * kLogChunk);
         res->ev_off[i + 1] = res->ev_off[i] + logged;
       }
-      const uint64_t total = res->ev_off[n_local];
-      if (total > 0) {
-        CUDA_TRY(cudaMalloc(&d_gather, sizeof(jsb_event) * total));
+      ev_total = res->ev_off[n_local];
+      ev_used_chunks = used_chunks;
+    }
+    {
+      // one pinned block for every bulk output
+      auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+      const size_t b_ev = up(sizeof(jsb_event) * ev_total);
+      const size_t b_lc = (opts->flags & JSB_OUT_LATTICE) ? up(sizeof(uint16_t) * (size_t)g->nv * n_local) : 0;
+      const size_t b_li = (opts->flags & JSB_OUT_LATTICE) ? up(sizeof(uint32_t) * (size_t)g->nv * n_local) : 0;
+      const size_t b_ls = (opts->flags & JSB_OUT_LISTS) ? up(sizeof(uint32_t) * 2 * (size_t)g->nv * n_local) : 0;
+      const size_t need = b_ev + b_lc + b_li + b_ls;
+      if (need > 0) {
+        res->pinned = pinned_take(need, &res->pinned_bytes);
+        if (!res->pinned) { rc = fail(JSB_ENOMEM, "cannot pin %llu bytes of host memory for the outputs", (unsigned long long)need); goto done; }
+        uint8_t* base = (uint8_t*)res->pinned;
+        res->events = (jsb_event*)base;
+        res->lat_clone = (uint16_t*)(base + b_ev);
+        res->lat_cell = (uint32_t*)(base + b_ev + b_lc);
+        res->lists = (uint32_t*)(base + b_ev + b_lc + b_li);
+      }
+      if (ev_total > 0) {
+        CUDA_TRY(cudaMalloc(&d_gather, sizeof(jsb_event) * ev_total));
         CUDA_TRY(cudaMalloc(&d_ev_off, sizeof(unsigned long long) * (n_local + 1)));
         CUDA_TRY(cudaMemcpyAsync(d_ev_off, res->ev_off.data(), sizeof(unsigned long long) * (n_local + 1), cudaMemcpyHostToDevice, stream));
-        int gblocks = (int)std::min<uint32_t>(used_chunks, (uint32_t)prop.multiProcessorCount * 8);
-        gather_log_kernel<<<gblocks, 256, 0, stream>>>(d_log, d_chunk_owner, d_chunk_seq, d_ev_off, used_chunks, d_gather);
+        int gblocks = (int)std::min<uint32_t>(ev_used_chunks, (uint32_t)prop.multiProcessorCount * 8);
+        gather_log_kernel<<<gblocks, 256, 0, stream>>>(d_log, d_chunk_owner, d_chunk_seq, d_ev_off, ev_used_chunks, d_gather);
         CUDA_TRY(cudaGetLastError());
         res->launches += 1;
-        res->events = (jsb_event*)pinned_take(sizeof(jsb_event) * total, &res->events_bytes);
-        if (!res->events) { rc = fail(JSB_ENOMEM, "cannot pin %llu bytes of host memory for the event log", (unsigned long long)(sizeof(jsb_event) * total)); goto done; }
-        CUDA_TRY(cudaMemcpyAsync(res->events, d_gather, sizeof(jsb_event) * total, cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaMemcpyAsync(res->events, d_gather, sizeof(jsb_event) * ev_total, cudaMemcpyDeviceToHost, stream));
       }
+      if (opts->flags & JSB_OUT_LATTICE) {
+        CUDA_TRY(cudaMemcpyAsync(res->lat_clone, d_out_clone, sizeof(uint16_t) * (size_t)g->nv * n_local, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(res->lat_cell, d_out_cell, sizeof(uint32_t) * (size_t)g->nv * n_local, cudaMemcpyDeviceToHost, stream));
+      }
+      if (opts->flags & JSB_OUT_LISTS)
+        CUDA_TRY(cudaMemcpyAsync(res->lists, d_out_lists, sizeof(uint32_t) * 2 * (size_t)g->nv * n_local, cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
     }
+    pt.mark("summaries + clones + log");
     if (max_snap > 0) {
       res->snaps.resize((size_t)max_snap * n_local);
       CUDA_TRY(cudaMemcpy(res->snaps.data(), d_snaps, sizeof(jsb_snapshot) * res->snaps.size(), cudaMemcpyDeviceToHost));
@@ -748,16 +801,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
         res->snap_count[i] = c;
       }
     }
-    if (opts->flags & JSB_OUT_LATTICE) {
-      res->lat_clone.resize((size_t)g->nv * n_local);
-      res->lat_cell.resize((size_t)g->nv * n_local);
-      CUDA_TRY(cudaMemcpy(res->lat_clone.data(), d_out_clone, sizeof(uint16_t) * res->lat_clone.size(), cudaMemcpyDeviceToHost));
-      CUDA_TRY(cudaMemcpy(res->lat_cell.data(), d_out_cell, sizeof(uint32_t) * res->lat_cell.size(), cudaMemcpyDeviceToHost));
-    }
-    if (opts->flags & JSB_OUT_LISTS) {
-      res->lists.resize(2 * (size_t)g->nv * n_local);
-      CUDA_TRY(cudaMemcpy(res->lists.data(), d_out_lists, sizeof(uint32_t) * res->lists.size(), cudaMemcpyDeviceToHost));
-    }
+    pt.mark("lattice + lists");
   }
 
 done:
@@ -769,6 +813,7 @@ done:
   if (ev1) cudaEventDestroy(ev1);
   if (stream) cudaStreamDestroy(stream);
   cudaSetDevice(prev_dev);
+  pt.mark("free");
   if (rc != JSB_OK) { delete res; return rc; }
   *out = res;
   return JSB_OK;
@@ -820,8 +865,8 @@ int jsb_result_events(jsb_result* r, int64_t i, const jsb_event** p, int64_t* n)
 int jsb_result_lattice(const jsb_result* r, int64_t i, const uint16_t** clone, const uint32_t** cell_id) {
   CHECK_INDEX(r, i);
   if (!(r->flags & JSB_OUT_LATTICE)) return fail(JSB_EINVAL, "run did not request JSB_OUT_LATTICE");
-  if (clone) *clone = r->lat_clone.data() + (size_t)i * r->nv;
-  if (cell_id) *cell_id = r->lat_cell.data() + (size_t)i * r->nv;
+  if (clone) *clone = r->lat_clone + (size_t)i * r->nv;
+  if (cell_id) *cell_id = r->lat_cell + (size_t)i * r->nv;
   return JSB_OK;
 }
 
@@ -831,7 +876,7 @@ int jsb_result_list(jsb_result* r, int64_t i, int32_t list, const uint32_t** p, 
   if (!(r->flags & JSB_OUT_LISTS)) return fail(JSB_EINVAL, "run did not request JSB_OUT_LISTS");
   const jsb_summary& s = r->summaries[i];
   if (list < 0 || list > (int32_t)s.n_clones) return fail(JSB_EINVAL, "list %d is outside 0..n_clones", list);
-  const uint32_t* base = r->lists.data() + (size_t)i * 2 * r->nv;
+  const uint32_t* base = r->lists + (size_t)i * 2 * r->nv;
   if (list == 0) { *p = base; *n = s.n_alive; return JSB_OK; }
   const jsb_clone* c;
   int32_t nc;

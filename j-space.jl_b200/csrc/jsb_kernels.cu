@@ -1582,7 +1582,7 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X) {
     if (r.status == JSB_ST_INTERNAL) break;
   }
 #ifdef JSB_PROFILE
-  if (lane == 0 && X.local_idx < 6) {
+  if (lane == 0 && (X.local_idx < 2 || r.it > 6000000ull)) {
     printf("rep %lld it %llu S %u n %u | refold %lld/%lld (elems %lld) draws %lld/%lld class %lld eval %lld time %lld | birth %lld/%lld death %lld/%lld migr %lld/%lld exc %lld\n",
            (long long)X.local_idx, (unsigned long long)r.it, r.S, r.n, prof_c[PH_REFOLD], prof_n[PH_REFOLD], prof_fold,
            prof_c[PH_DRAWS], prof_n[PH_DRAWS], prof_c[PH_CLASS], prof_c[PH_EVAL], prof_c[PH_TIME], prof_c[PH_BIRTH],
