@@ -219,6 +219,7 @@ struct Ctx {
   double* B;                // per-warp shared slice: class boundaries [kSmemTable]
   uint32_t* occ;            // per-warp shared occupancy bitmask (nullptr: test clone[] in global)
   uint32_t sB, sLen, sOff, sOcc;  // the same slices as 32-bit shared-window addresses (sOcc = 0: none)
+  uint32_t sDt;             // 32 doubles: per-lane time increments of the current window
   uint32_t search_top;      // power of two >= S+2: first probe distance of the class search
   Key key;
   int64_t local_idx;
@@ -819,8 +820,9 @@ __device__ __forceinline__ bool eval_target(const Ctx<T>& X, const Rep& r, uint6
 // One speculative window of U sub-batches: lane l of sub-batch u evaluates iteration
 // it + 1 + 32u + l against the current state.  effm[u] = ballot of state-changing lanes.
 // Measured on B200 (C2 ensemble): windows of 2-4 sub-batches per lane cut single-replicate latency
-// by only ~8 % and cost 30-60 % throughput in wasted speculation, so the window stays at one
-// sub-batch; the multi-sub-batch path is kept for experiments (kAdaptiveWindow).
+// by only ~8 % and cost 30-60 % throughput in wasted speculation (ptxas does not interleave the
+// sub-batches; a 2-wide window used only after an all-null window was 25 % slower overall), so the
+// window stays at one sub-batch; the multi-sub-batch path is kept for experiments.
 constexpr int kMaxSub = 4;
 constexpr bool kAdaptiveWindow = false;
 template <typename T, int U>
@@ -874,15 +876,21 @@ __device__ __forceinline__ void batch_eval(Ctx<T>& X, Rep& r, bool force_exact, 
   }
 }
 
-// sequential t += dt over lanes 0..last of one sub-batch (:701)
-__device__ __forceinline__ double time_chain(double t, double dt, uint32_t last) {
+// sequential t += dt over lanes 0..last of one sub-batch (:701).  The increments are staged in
+// shared memory so that the chain is nothing but dependent fp64 adds (broadcast loads, issued
+// ahead); through shuffles every step also paid the shuffle latency.
+__device__ __forceinline__ double time_chain(uint32_t sDt, int lane, double t, double dt, uint32_t last) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(sDt + (uint32_t)lane * 8u), "d"(dt) : "memory");
+  __syncwarp();
   uint32_t l = 0;
-  for (; l + 4 <= last + 1; l += 4) {  // shuffles issue back to back, the adds stay sequential
-    double d0 = __shfl_sync(FULL, dt, (int)l), d1 = __shfl_sync(FULL, dt, (int)l + 1);
-    double d2 = __shfl_sync(FULL, dt, (int)l + 2), d3 = __shfl_sync(FULL, dt, (int)l + 3);
+  for (; l + 4 <= last + 1; l += 4) {
+    double d0, d1, d2, d3;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(d0), "=d"(d1) : "r"(sDt + l * 8u) : "memory");
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(d2), "=d"(d3) : "r"(sDt + l * 8u + 16u) : "memory");
     t = t + d0; t = t + d1; t = t + d2; t = t + d3;
   }
-  for (; l <= last; ++l) t = t + __shfl_sync(FULL, dt, (int)l);
+  for (; l <= last; ++l) t = t + lds_f64(sDt + l * 8u);
+  __syncwarp();
   return t;
 }
 
@@ -1482,7 +1490,7 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X) {
     double tend = r.t;
 #pragma unroll
     for (int u = 0; u < kMaxSub; ++u)
-      if ((uint32_t)u <= ustar && (uint32_t)u < Ucur) tend = time_chain(tend, dtv[u], (uint32_t)u == ustar ? jE : 31u);
+      if ((uint32_t)u <= ustar && (uint32_t)u < Ucur) tend = time_chain(X.sDt, lane, tend, dtv[u], (uint32_t)u == ustar ? jE : 31u);
 
     // ---- can anything other than that one event happen in (t, tend]? ---------------------------
     auto touches = [&](double t1, uint64_t n_commit) -> bool {
@@ -1506,7 +1514,7 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X) {
       ustar = 0;
       found = effm[0] != 0;
       jE = found ? (uint32_t)__ffs(effm[0]) - 1u : 31u;
-      tend = time_chain(r.t, dtv[0], jE);
+      tend = time_chain(X.sDt, lane, r.t, dtv[0], jE);
       slow = touches(tend, (uint64_t)jE + 1u);
       Ucur = 1;
     } else if (kAdaptiveWindow && width == 32u) {
@@ -1598,9 +1606,9 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X) {
 }
 
 // Per-warp shared-memory slice:
-//   [ B: kSmemTable doubles | c_len: kTab u32 | c_off: kTab u32 | DevPoint | occupancy bits ]
+//   [ B: kSmemTable doubles | dt staging: 32 doubles | c_len: kTab u32 | c_off: kTab u32 | DevPoint | occupancy bits ]
 __host__ __device__ inline size_t smem_base_bytes() {
-  return sizeof(double) * kSmemTable + 2 * sizeof(uint32_t) * kTab + ((sizeof(DevPoint) + 15) & ~size_t(15));
+  return sizeof(double) * (kSmemTable + 32) + 2 * sizeof(uint32_t) * kTab + ((sizeof(DevPoint) + 15) & ~size_t(15));
 }
 
 template <typename T>
@@ -1628,11 +1636,12 @@ __global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __
   X.g_w = reinterpret_cast<double*>(base + L.g_w);
   X.g_c = reinterpret_cast<double*>(base + L.g_c);
   X.B = reinterpret_cast<double*>(sw);
-  X.c_len = reinterpret_cast<uint32_t*>(sw + sizeof(double) * kSmemTable);
+  X.c_len = reinterpret_cast<uint32_t*>(sw + sizeof(double) * (kSmemTable + 32));
   X.c_off = X.c_len + kTab;
   DevPoint* sP = reinterpret_cast<DevPoint*>(X.c_off + kTab);
   X.occ = A.occ_words ? reinterpret_cast<uint32_t*>(sw + smem_base_bytes()) : nullptr;
   X.sB = smem_addr(X.B);
+  X.sDt = X.sB + 8u * kSmemTable;
   X.sLen = smem_addr(X.c_len);
   X.sOff = smem_addr(X.c_off);
   X.sOcc = X.occ ? smem_addr(X.occ) : 0u;
