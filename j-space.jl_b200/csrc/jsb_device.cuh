@@ -52,7 +52,7 @@ struct DevPoint {
 
 // Workspace layout per slot (all offsets 16-byte aligned); computed identically on host and device.
 struct WsLayout {
-  uint64_t clone, cellid, A, arena, inds, samp, c_off, c_len, c_cap, c_alpha, c_parent, c_label, g_B, g_w, g_c,
+  uint64_t clone, cellid, A, a_head, arena, inds, samp, c_off, c_len, c_cap, c_alpha, c_parent, c_label, g_B, g_w, g_c,
       total;
 };
 struct RunArgs {
@@ -105,7 +105,8 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t nv, uint32_t arena_cap, u
   uint64_t o = 0;
   L.clone = o;    o = jsb_align16(o + 2ull * nv);
   L.cellid = o;   o = jsb_align16(o + 4ull * nv);
-  L.A = o;        o = jsb_align16(o + (uint64_t)site_bytes * (nv + 1) + 32);   // +32: vector-shift read slack
+  L.A = o;        o = jsb_align16(o + (uint64_t)site_bytes * ((uint64_t)nv + 1 + 512));  // tiered vector: whole segments of 256
+  L.a_head = o;   o = jsb_align16(o + 2ull * (nv / 256 + 4));
   L.arena = o;    o = jsb_align16(o + (uint64_t)site_bytes * arena_cap + 32);
   L.inds = o;     o = jsb_align16(o + 4ull * nv);
   L.samp = o;     o = jsb_align16(o + 4ull * nv);

@@ -210,6 +210,7 @@ struct Ctx {
   uint16_t* clone;
   uint32_t* cellid;
   T *Alist, *arena;
+  uint16_t* a_head;         // tiered-vector segment heads of cs_alive
   uint32_t *inds, *samp;
   uint32_t *c_off, *c_len;  // per-warp shared slices [kMaxClones]
   uint32_t* c_cap;          // global; capacities are powers of two >= kMinListCap
@@ -522,6 +523,76 @@ __device__ __noinline__ void arena_gc(Ctx<T>& X, Rep& r) {
   r.arena_top = total;
 }
 
+// ---------------------------------------------------------------------------------------------
+// cs_alive as a tiered vector (Goodrich & Kloss): fixed segments of kSeg elements, each a circular
+// buffer with its own head; every segment but the last is full.  Element p lives in segment
+// p / kSeg at offset (head + p % kSeg) mod kSeg, so `cs_alive[x]` stays O(1), and the stable delete
+// filter!(e -> e != cell, cs_alive) moves at most kSeg elements inside one segment plus ONE element
+// per following segment (its front becomes the previous segment's back) instead of shifting the
+// whole tail: ~n/2 elements (40 KB at n = 20 000) -> a few hundred bytes.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kSeg = 256;
+
+template <typename T>
+__device__ __forceinline__ uint32_t a_slot(const Ctx<T>& X, uint32_t p) {
+  const uint32_t s = p / kSeg;
+  return s * kSeg + ((X.a_head[s] + (p & (kSeg - 1u))) & (kSeg - 1u));
+}
+template <typename T>
+__device__ __forceinline__ uint32_t a_get(const Ctx<T>& X, uint32_t p) { return (uint32_t)X.Alist[a_slot(X, p)]; }
+
+// push!(cs_alive, site) with n elements present (single lane)
+template <typename T>
+__device__ __forceinline__ void a_append(const Ctx<T>& X, uint32_t n, uint32_t site) {
+  const uint32_t s = n / kSeg;
+  if ((n & (kSeg - 1u)) == 0) X.a_head[s] = 0;
+  X.Alist[s * kSeg + ((X.a_head[s] + (n & (kSeg - 1u))) & (kSeg - 1u))] = (T)site;
+}
+
+// remove logical element p of n, keep order (whole warp)
+template <typename T>
+__device__ __noinline__ void a_remove(T* A, uint16_t* head, uint32_t n, uint32_t p, int lane) {
+  const uint32_t s = p / kSeg, i = p & (kSeg - 1u);
+  const uint32_t ls = (n - 1) / kSeg;                       // last segment
+  const uint32_t cnt = (s == ls) ? ((n - 1) & (kSeg - 1u)) + 1u : kSeg;
+  const uint32_t hs = head[s];
+  T* seg = A + s * kSeg;
+  // inside segment s: logical j <- j+1 for j in [i, cnt-1)
+  for (uint32_t base = i; base + 1 < cnt; base += 32) {
+    const uint32_t j = base + lane;
+    T v = 0;
+    const bool act = j + 1 < cnt;
+    if (act) v = seg[(hs + j + 1) & (kSeg - 1u)];
+    __syncwarp();
+    if (act) seg[(hs + j) & (kSeg - 1u)] = v;
+    __syncwarp();
+  }
+  // every later segment hands its front to the back of its predecessor and rotates by one
+  uint32_t prev_head_carry = hs;  // head of segment t-1 before this call, for the first lane
+  for (uint32_t base = s + 1; base <= ls; base += 32) {
+    const uint32_t t = base + lane;
+    const bool act = t <= ls;
+    uint32_t ht = 0, hp = 0;
+    T v = 0;
+    if (act) {
+      ht = head[t];
+      hp = (lane == 0) ? prev_head_carry : (uint32_t)head[t - 1];
+      v = A[t * kSeg + ht];
+    }
+    const uint32_t last_ht = __shfl_sync(FULL, ht, 31);
+    __syncwarp();
+    if (act) {
+      // back slot of t-1: segment s kept its head (slot head+kSeg-1); later ones rotated, so their
+      // new back is their old front slot
+      const uint32_t slot = (t - 1 == s) ? ((hs + kSeg - 1u) & (kSeg - 1u)) : hp;
+      A[(t - 1) * kSeg + slot] = v;
+      head[t] = (uint16_t)((ht + 1u) & (kSeg - 1u));
+    }
+    prev_head_carry = last_ht;
+    __syncwarp();
+  }
+}
+
 // slow path of list_append: list c is full
 template <typename T>
 __device__ __noinline__ bool list_grow(Ctx<T>& X, Rep& r, uint32_t c) {
@@ -770,7 +841,7 @@ __device__ __forceinline__ void eval_member(const Ctx<T>& X, const Rep& r, uint6
   const bool is_birth = cls < S;
   const uint32_t ci = is_birth ? cls : 0u;
   const uint32_t off = lds_u32(X.sOff + ci * 4u), cl = lds_u32(X.sLen + ci * 4u);
-  const T* list = is_birth ? X.arena + off : X.Alist;
+  const T* list = X.arena + off;
   const uint32_t llen = is_birth ? cl : r.n;
   // cls >= S+2: findfirst -> nothing in the reference; llen == 0: rand(1:0) throws.  Contract:
   // both are null iterations.
@@ -779,7 +850,7 @@ __device__ __forceinline__ void eval_member(const Ctx<T>& X, const Rep& r, uint6
   cell = 0;
   if (valid) {
     x = bounded(X.key, w_cell, llen, q, DS_CELL_NBR, 0, 0);  // :727 / :746 / :762
-    cell = (uint32_t)list[x];
+    cell = is_birth ? (uint32_t)list[x] : a_get(X, x);
   }
 }
 
@@ -906,14 +977,14 @@ __device__ __forceinline__ void apply_migration(Ctx<T>& X, Rep& r, const Eval& e
     X.clone[e.cell] = 0;
     X.clone[e.pos] = (uint16_t)cl;
     if (X.track_ids) X.cellid[e.pos] = cid;
-    X.Alist[r.n] = (T)e.pos;  // push!(cs_alive, pos)
+    a_append(X, r.n, e.pos);  // push!(cs_alive, pos)
     occ_clear(X.occ, e.cell);
     occ_set(X.occ, e.pos);
   }
   __syncwarp();
   log_row(X, r, JSB_EV_MIGRATION, JSB_EVF_GROUP_START, r.t, cid, 0, e.pos, e.cell + 1, cl, 0);
   list_append(X, r, cl - 1, e.pos);                   // push!(ca_subpop[idx], pos)
-  list_remove_at<T>(X.Alist, r.n + 1, e.x, X.lane);   // filter!(e -> e != cell, cs_alive)
+  a_remove<T>(X.Alist, X.a_head, r.n + 1, e.x, X.lane);  // filter!(e -> e != cell, cs_alive)
   list_remove_value(X, cl - 1, e.cell);               // filter!(e -> e != cell, ca_subpop[idx])
   r.n_eff++;
   r.n_migr++;
@@ -927,7 +998,7 @@ __device__ __forceinline__ void apply_death(Ctx<T>& X, Rep& r, const Eval& e) { 
   log_row(X, r, JSB_EV_DEATH, JSB_EVF_GROUP_START, r.t, cid, 0, e.cell, 0, cl, 0);
   if (X.lane == 0) { X.clone[e.cell] = 0; occ_clear(X.occ, e.cell); }
   __syncwarp();
-  list_remove_at<T>(X.Alist, r.n, e.x, X.lane);
+  a_remove<T>(X.Alist, X.a_head, r.n, e.x, X.lane);
   list_remove_value(X, cl - 1, e.cell);
   r.n -= 1;
   r.n_eff++;
@@ -1075,7 +1146,7 @@ __device__ __forceinline__ bool apply_birth(Ctx<T>& X, Rep& r, const Eval& e) {
     }
   }
   if (e.occ == 0) {  // :803-806
-    if (X.lane == 0) { X.Alist[r.n] = (T)e.pos; occ_set(X.occ, e.pos); }
+    if (X.lane == 0) { a_append(X, r.n, e.pos); occ_set(X.occ, e.pos); }
     __syncwarp();
     r.n += 1;
     mark_dirty(r, r.S);  // death and migration weights changed (B_S, B_{S+1})
@@ -1102,7 +1173,7 @@ __device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double
     uint64_t a, b;
     draw_block_nl(X.key, r.it, 0, DS_EXCISION, 0, a, b);
     uint32_t i = bounded(X.key, a, n, r.it, DS_EXCISION, 0, 0);
-    if (lane == 0) samp[0] = (uint32_t)X.Alist[i];
+    if (lane == 0) samp[0] = a_get(X, i);
   } else if (k == 2) {  // samplepair
     uint64_t a, b;
     draw_block_nl(X.key, r.it, 0, DS_EXCISION, 0, a, b);
@@ -1110,8 +1181,8 @@ __device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double
     draw_block_nl(X.key, r.it, 0, DS_EXCISION, 1, a, b);
     uint32_t i2 = bounded(X.key, a, n - 1, r.it, DS_EXCISION, 1, 0) + 1;
     if (lane == 0) {
-      samp[0] = (uint32_t)X.Alist[i1 - 1];
-      samp[1] = (uint32_t)X.Alist[(i2 == i1 ? n : i2) - 1];
+      samp[0] = a_get(X, i1 - 1);
+      samp[1] = a_get(X, (i2 == i1 ? n : i2) - 1);
     }
   } else if (k > 2 && (unsigned long long)n < (unsigned long long)k * 24ull) {  // fisher_yates_sample!
     for (uint32_t i = lane; i < n; i += 32) inds[i] = i;
@@ -1132,7 +1203,7 @@ __device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double
           uint32_t tj = inds[j], ti = inds[ii];
           inds[j] = ti;
           inds[ii] = tj;
-          samp[ii] = (uint32_t)X.Alist[tj];
+          samp[ii] = a_get(X, tj);
         }
       }
       __syncwarp();
@@ -1152,7 +1223,7 @@ __device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double
           if (!inds[idx]) break;
         }
         inds[idx] = 1;
-        samp[i] = (uint32_t)X.Alist[idx];
+        samp[i] = a_get(X, idx);
       }
     }
   }
@@ -1190,19 +1261,23 @@ __device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double
   if (X.occ && lane == 0)
     for (uint32_t i = 0; i < k; ++i) occ_clear(X.occ, samp[i]);
   __syncwarp();
-  // stable compaction of cs_alive and of every ca_subpop list (== the sequence of filter! calls)
+  // stable compaction of cs_alive and of every ca_subpop list (== the sequence of filter! calls).
+  // cs_alive is rebuilt as a fresh tiered vector (all heads 0) through the scratch array.
   {
     uint32_t wpos = 0;
     for (uint32_t base = 0; base < n; base += 32) {
       uint32_t i = base + lane;
-      T v = 0;
+      uint32_t v = 0;
       bool keep = false;
-      if (i < n) { v = X.Alist[i]; keep = X.clone[v] != 0; }
+      if (i < n) { v = a_get(X, i); keep = X.clone[v] != 0; }
       uint32_t m = __ballot_sync(FULL, keep);
-      if (keep) X.Alist[wpos + __popc(m & ((1u << lane) - 1u))] = v;
+      if (keep) inds[wpos + __popc(m & ((1u << lane) - 1u))] = v;
       wpos += __popc(m);
-      __syncwarp();
     }
+    __syncwarp();
+    for (uint32_t i = lane; i < wpos; i += 32) X.Alist[i] = (T)inds[i];
+    for (uint32_t sg = lane; sg * kSeg <= wpos; sg += 32) X.a_head[sg] = 0;
+    __syncwarp();
   }
   for (uint32_t c = 0; c < r.S; ++c) {
     uint32_t len = X.c_len[c];
@@ -1239,6 +1314,7 @@ __device__ __noinline__ void seed_replicate(Ctx<T>& X, Rep& r) {
   if (X.occ)
     for (uint32_t i = lane; i < X.A->occ_words; i += 32) X.occ[i] = 0;
   for (uint32_t i = lane; i < (uint32_t)kSmemTable; i += 32) X.B[i] = __longlong_as_double(0x7ff0000000000000ll);  // +inf pad
+  for (uint32_t sg = lane; sg * kSeg <= (uint32_t)(P.n_start > 1 ? P.n_start : 1); sg += 32) X.a_head[sg] = 0;
   __syncwarp();
   uint32_t n0 = 0;
   if (P.n_start == 1) {
@@ -1360,7 +1436,7 @@ __device__ __noinline__ void write_outputs(Ctx<T>& X, Rep& r) {
   if (A.out_lists) {
     uint32_t* la = A.out_lists + (size_t)X.local_idx * 2 * nv;
     uint32_t* ll = la + nv;
-    for (uint32_t i = lane; i < r.n; i += 32) la[i] = (uint32_t)X.Alist[i] + 1;
+    for (uint32_t i = lane; i < r.n; i += 32) la[i] = a_get(X, i) + 1;
     uint32_t wpos = 0;
     for (uint32_t c = 0; c < r.S; ++c) {
       uint32_t len = X.c_len[c];
@@ -1627,6 +1703,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __
   X.cellid = reinterpret_cast<uint32_t*>(base + L.cellid);
   X.Alist = reinterpret_cast<T*>(base + L.A);
   X.arena = reinterpret_cast<T*>(base + L.arena);
+  X.a_head = reinterpret_cast<uint16_t*>(base + L.a_head);
   X.inds = reinterpret_cast<uint32_t*>(base + L.inds);
   X.samp = reinterpret_cast<uint32_t*>(base + L.samp);
   X.c_cap = reinterpret_cast<uint32_t*>(base + L.c_cap);
