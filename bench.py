@@ -46,6 +46,9 @@ WORKLOADS = {
 BASE_SEED = 1234
 # algorithmic bytes per loop iteration, SURVEY.md §8(d)
 A_NULL, A_BIRTH, A_DEATH = 6.0, 78.0, 46.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one ssa_kernel launch of workload C2 (4096 replicates),
+# from the ncu pass committed as profiles/r1_bench_c2_launches.csv (52.27 GB read + 42.56 GB written)
+MEASURED_TRAFFIC = {("C2", 4096): 94833735168}
 
 
 def measured_peak_gbs():
@@ -324,7 +327,7 @@ def main():
             "effective_events_per_s": all_eff / (max_ms / 1e3),
             "wall_s": wall,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": MEASURED_TRAFFIC.get((args.workload, reps)), "peak_source": peak_src,
                          "note": "latency-bound SSA: algorithmic bytes 6 B/iteration + 78 B/birth + 46 B/death "
                                  "(SURVEY 8d); see profiles/ for issue-slot utilisation and stall reasons"},
             "cpu_baseline": cpu,
