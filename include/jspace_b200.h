@@ -67,6 +67,13 @@ extern "C" {
 #define JSB_OUT_EVENTS 0x1u  /* keep the per-replicate event log (`df`)                   */
 #define JSB_OUT_LATTICE 0x2u /* keep the final lattice (clone id + cell id per site)      */
 #define JSB_OUT_LISTS 0x4u   /* keep the final ordered cs_alive / ca_subpop lists          */
+/* ---- simulation mode (jsb_run_opts.flags) ------------------------------------------------
+ * JSB_MODE_REJECTION_FREE: same stochastic law, different algorithm.  Null
+ * events are not simulated: a per-site propensity tree selects only state-changing events and
+ * time advances by Exp(total effective rate).  Trajectories are NOT comparable event for event
+ * with the reference (validated by two-sample KS tests on ensemble statistics); n_iterations
+ * then counts effective events; ordered lists (JSB_OUT_LISTS) do not exist in this mode.     */
+#define JSB_MODE_REJECTION_FREE 0x100u
 
 /* ---- event log record: one row of the reference's `df` (src/J_Space.jl:284-290) -------
  * Rows appear in exactly the reference's push! order (cell_birth :351-352 / :387-388,

@@ -501,6 +501,12 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
   if ((double)n_points * (double)reps_per_point > 4294967295.0) return fail(JSB_ECAPACITY, "more than 2^32-1 replicates");
   const int64_t g_total = n_points * reps_per_point;
   int64_t g_begin = opts->g_begin, g_end = opts->g_end == 0 ? g_total : opts->g_end;
+  if ((opts->flags & JSB_MODE_REJECTION_FREE) && (opts->flags & JSB_OUT_LISTS)) return fail(JSB_EINVAL, "JSB_OUT_LISTS is not available with JSB_MODE_REJECTION_FREE (no ordered lists exist in that mode)");
+  if ((opts->flags & JSB_MODE_REJECTION_FREE) && g->kind == 1) {
+    uint32_t maxdeg = 0;
+    for (int64_t v = 0; v < g->nv; ++v) maxdeg = std::max(maxdeg, g->rowptr[v + 1] - g->rowptr[v]);
+    if (maxdeg > 32) return fail(JSB_ECAPACITY, "JSB_MODE_REJECTION_FREE supports vertex degrees up to 32 (graph has %u)", maxdeg);
+  }
   if (g_begin < 0 || g_end > g_total || g_begin > g_end) return fail(JSB_EINVAL, "replicate range [%lld,%lld) is outside [0,%lld)", (long long)g_begin, (long long)g_end, (long long)g_total);
   bool need_closeness = false;
   for (int64_t i = 0; i < n_points; ++i) {
@@ -609,8 +615,9 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     std::memset(&a, 0, sizeof a);
     a.g.nv = (uint32_t)g->nv;
     a.site_bytes = g->nv <= 65536 ? 2u : 4u;
+    const bool fast_mode = (opts->flags & JSB_MODE_REJECTION_FREE) != 0;
     int wpb = 1;
-    if (ssa_prepare(a, opts->warps_per_sm, &wpb) != 0) { rc = fail(JSB_ECUDA, "cannot configure shared memory for the SSA kernel"); goto done; }
+    if ((fast_mode ? fast_prepare(a, opts->warps_per_sm, &wpb) : ssa_prepare(a, opts->warps_per_sm, &wpb)) != 0) { rc = fail(JSB_ECUDA, "cannot configure shared memory for the SSA kernel"); goto done; }
     // one block per SM; spread small ensembles over all SMs before stacking warps
     {
       int64_t per_sm = (n_local + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
@@ -690,7 +697,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     // replicate; its work estimate has rank correlation ~0.97 with the final iteration counts)
     // orders the full pass longest first.  Off by default: on the C2 ensemble the kernel time is
     // the latency of the single heaviest replicate (measured: 2.82 s with, 2.76 s without).
-    if ((uint64_t)n_local > slots && (uint64_t)n_local <= 16 * slots && std::getenv("JSB_PILOT")) {
+    if (!fast_mode && (uint64_t)n_local > slots && (uint64_t)n_local <= 16 * slots && std::getenv("JSB_PILOT")) {
       CUDA_TRY(cudaMalloc(&d_prio, sizeof(float) * n_local));
       CUDA_TRY(cudaMalloc(&d_order, sizeof(uint32_t) * n_local));
       RunArgs pa = a;
@@ -714,7 +721,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
       a.order = d_order;
     }
     {
-      int lrc = launch_ssa(a, grid, wpb, stream);
+      int lrc = fast_mode ? launch_fast(a, grid, wpb, stream) : launch_ssa(a, grid, wpb, stream);
       if (lrc != 0) { rc = fail(JSB_ECUDA, "kernel launch failed: %s", cudaGetErrorString((cudaError_t)lrc)); goto done; }
     }
     res->launches += 1;

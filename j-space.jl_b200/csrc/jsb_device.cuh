@@ -53,7 +53,7 @@ struct DevPoint {
 // Workspace layout per slot (all offsets 16-byte aligned); computed identically on host and device.
 struct WsLayout {
   uint64_t clone, cellid, A, a_head, arena, inds, samp, c_off, c_len, c_cap, c_alpha, c_parent, c_label, g_B, g_w, g_c,
-      total;
+      ftree, total;
 };
 struct RunArgs {
   DevGraph g;
@@ -94,6 +94,7 @@ struct RunArgs {
   unsigned long long* work_counter;
   // longest-first scheduling: a pilot pass runs every replicate for `pilot_iters`
   // iterations and writes a work estimate; the full pass then takes replicates in `order`
+  uint32_t fast_smem_tree;  // rejection-free mode: upper tree levels live in shared memory
   const uint32_t* order;  // nullptr: natural order
   uint64_t pilot_iters;   // > 0: pilot pass (no outputs except prio)
   float* prio;
@@ -119,12 +120,15 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t nv, uint32_t arena_cap, u
   L.g_B = o;      o = jsb_align16(o + 8ull * (kTab + 8));
   L.g_w = o;      o = jsb_align16(o + 8ull * (kTab + 8));
   L.g_c = o;      o = jsb_align16(o + 8ull * (kTab + 8));
+  L.ftree = o;    o = jsb_align16(o + 8ull * ((uint64_t)nv / 31 + 128));  // fast mode: upper tree levels (geometric sum)
   L.total = (o + 255) & ~uint64_t(255);
   return L;
 }
 
 // host-callable launch wrapper (jsb_kernels.cu)
 int launch_ssa(const RunArgs& args, int grid_blocks, int warps_per_block, void* stream);
+int fast_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block);
+int launch_fast(const RunArgs& args, int grid_blocks, int warps_per_block, void* stream);
 int ssa_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block);  // fills occ_words / smem_per_warp
 
 }  // namespace jsb

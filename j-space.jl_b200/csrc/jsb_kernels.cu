@@ -1794,4 +1794,847 @@ int launch_ssa(const RunArgs& args, int grid_blocks, int warps_per_block, void* 
   return (int)cudaGetLastError();
 }
 
+
+// =================================================================================================
+// Rejection-free mode (JSB_MODE_REJECTION_FREE)
+//
+// Same stochastic law as the reference loop, different algorithm.  In the reference a cell of clone
+// c is picked at rate α_c, a uniform neighbour is drawn and the event is rejected unless the contact
+// rule admits it (src/J_Space.jl:762-786); 79-99 % of iterations are such null events.  By the
+// thinning property the state-changing events form a process in which cell v fires at rate
+//     p_v = α_c·adm_v/deg_v  (birth into a uniformly chosen admissible neighbour)
+//         + rate_death
+//         + rate_migration·emp_v/deg_v  (move to a uniformly chosen empty neighbour)
+// and time advances by Exp(Σ_v p_v) between them.  p_v sits in a 32-ary sum tree: leaves (one fp64
+// per site) in HBM, every upper level in shared memory; a warp selects an event by one 32-wide
+// scan + ballot per level and updates the ≤ deg+1 sites around a changed site with shared-memory
+// atomics.  Upper levels are re-summed from the leaves every kFastRebuild events (rounding drift).
+//
+// What the reference does at Tf, at an excision time and for snapshots depends on the (invisible)
+// null iterations; that is reproduced in law: given the next state-changing event at t' and a
+// boundary τ in (t, t'), the event belongs to the loop iteration that crosses τ with probability
+// exp(−ν (t' − τ)), ν = λ_reference − Σ p_v being the null-iteration rate.
+// =================================================================================================
+constexpr int kFastLevels = 6;        // 32^6 > 2^28 sites
+constexpr uint32_t kFastRebuild = 2048;
+enum : uint32_t { DS_F_TIME_SELECT = 12, DS_F_KIND_NBR = 13, DS_F_BOUNDARY = 11 };
+
+struct FCtx {
+  const RunArgs* A;
+  const DevPoint* P;
+  const double *tb, *ratio, *tsnap, *node_rate;
+  const int32_t *edge_parent, *edge_child;
+  uint16_t* clone;
+  uint32_t* cellid;
+  uint32_t *inds, *samp;
+  double* lvl[kFastLevels];  // lvl[0] = per-site rates, lvl[k][i] = sum of lvl[k-1][32i .. 32i+31]
+  uint32_t lvl_n[kFastLevels];
+  int top;                   // lvl[top] has at most 32 entries
+  uint32_t* c_cnt;
+  double* c_alpha;
+  uint16_t *c_parent, *c_label;
+  Key key;
+  int64_t local_idx;
+  int lane;
+  bool track_ids;
+};
+
+struct FRep {
+  double t, wsum;  // wsum = Σ α_c·n_c (the birth part of the reference's λ)
+  uint64_t it, nlog;
+  uint32_t n, S, next_id, cur_chunk, used_w, since_rebuild;
+  int bott_id, snap_idx, status;
+  uint32_t n_births, n_deaths, n_migr, n_disp, n_exc;
+  bool log_on;
+};
+
+// Neighbourhood of site s in "slots": lattice slot = direction bit (z-1, y-1, x-1, x+1, y+1, z+1),
+// CSR slot = position in the row (degree <= 32 in this mode).  One gather: the site's own clone and
+// the clones on all neighbours are loaded together.
+struct FHood {
+  uint32_t own;       // clone on s (0 = empty)
+  uint32_t present;   // slots that exist
+  uint32_t empty;     // slots whose neighbour is empty
+  uint32_t cw[6];     // lattice: clone per direction (statically indexed: registers)
+  uint32_t cwl[32];   // CSR: clone per row position (dynamically indexed: local memory)
+};
+
+__device__ __forceinline__ uint32_t f_slot_site(const FCtx& X, uint32_t s, uint32_t slot) {
+  const DevGraph& g = X.A->g;
+  if (g.kind == 0) {
+    const int plane = (int)(g.n1 * g.n2), n1 = (int)g.n1;
+    const int d = slot == 0 ? -plane : slot == 1 ? -n1 : slot == 2 ? -1 : slot == 3 ? 1 : slot == 4 ? n1 : plane;
+    return (uint32_t)((int)s + d);
+  }
+  return g.colidx[g.rowptr[s] + slot];
+}
+
+__device__ __forceinline__ void f_gather(const FCtx& X, uint32_t s, FHood& h) {
+  const DevGraph& g = X.A->g;
+  h.own = X.clone[s];
+  h.empty = 0;
+  if (g.kind == 0) {
+    const uint32_t mask = lattice_mask(g, s);
+    const int plane = (int)(g.n1 * g.n2), n1 = (int)g.n1;
+    const int delta[6] = {-plane, -n1, -1, 1, n1, plane};
+#pragma unroll
+    for (int b = 0; b < 6; ++b) h.cw[b] = ((mask >> b) & 1u) ? (uint32_t)X.clone[(uint32_t)((int)s + delta[b])] : 0u;
+#pragma unroll
+    for (int b = 0; b < 6; ++b)
+      if (((mask >> b) & 1u) && h.cw[b] == 0) h.empty |= 1u << b;
+    h.present = mask;
+    return;
+  }
+  const uint32_t row0 = g.rowptr[s];
+  uint32_t deg = g.rowptr[s + 1] - row0;
+  if (deg > 32) deg = 32;
+  h.present = deg == 32 ? FULL : ((1u << deg) - 1u);
+  for (uint32_t base = 0; base < deg; base += 8) {
+    uint32_t nb[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) nb[q] = base + q < deg ? g.colidx[row0 + base + q] : 0u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (base + q < deg) {
+        const uint32_t c = X.clone[nb[q]];
+        h.cwl[base + q] = c;
+        if (c == 0) h.empty |= 1u << (base + q);
+      }
+  }
+}
+
+// may a cell of clone c divide onto a neighbour holding clone cw (0 = empty)?  :767-786
+__device__ __forceinline__ bool f_admissible(const FCtx& X, uint32_t c, uint32_t cw) {
+  if (cw == 0) return true;
+  const int model = X.P->rule;
+  if (model == JSB_RULE_CONTACT) return false;
+  if (model == JSB_RULE_VOTER) return cw != c;
+  if (model == JSB_RULE_HVOTER) return !(X.c_alpha[c - 1] <= X.c_alpha[cw - 1]);
+  return true;
+}
+
+// slots a cell of clone h.own may divide onto
+__device__ __forceinline__ uint32_t f_adm_mask(const FCtx& X, const FHood& h) {
+  if (h.own == 0) return 0;  // an empty site divides nowhere (and has no fitness to compare)
+  if (X.P->rule == JSB_RULE_CONTACT) return h.empty;
+  uint32_t m = 0;
+  if (X.A->g.kind == 0) {
+#pragma unroll
+    for (int b = 0; b < 6; ++b)
+      if (((h.present >> b) & 1u) && f_admissible(X, h.own, h.cw[b])) m |= 1u << b;
+  } else {
+    for (uint32_t b = 0; b < 32 && ((h.present >> b) & 1u); ++b)
+      if (f_admissible(X, h.own, h.cwl[b])) m |= 1u << b;
+  }
+  return m;
+}
+
+// rate of a site from its gathered neighbourhood
+__device__ __forceinline__ double f_rate(const FCtx& X, const FHood& h, uint32_t adm_mask, double& bpart) {
+  bpart = 0.0;
+  if (h.own == 0) return 0.0;
+  const uint32_t deg = (uint32_t)__popc(h.present);
+  double mpart = 0.0;
+  if (deg > 0) {
+    bpart = X.c_alpha[h.own - 1] * (double)__popc(adm_mask) / (double)deg;
+    mpart = X.P->rate_migration * (double)__popc(h.empty) / (double)deg;
+  }
+  return bpart + X.P->rate_death + mpart;
+}
+
+// add `delta` to a tree entry: native shared-memory reduction when the level lives in shared memory
+__device__ __forceinline__ void f_tree_add(double* p, bool in_smem, double delta) {
+  if (in_smem) asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(smem_addr(p)), "d"(delta) : "memory");
+  else atomicAdd(p, delta);
+}
+
+// site c changed: recompute the rates of c and of all its neighbours (lane 0: c, lane 1+slot: the
+// neighbour in that slot; the candidates of one call are distinct, so no de-duplication is needed)
+__device__ __forceinline__ void f_refresh_around(const FCtx& X, uint32_t c) {
+  const DevGraph& g = X.A->g;
+  const int lane = X.lane;
+  uint32_t present;
+  if (g.kind == 0) present = lattice_mask(g, c);
+  else {
+    uint32_t deg = g.rowptr[c + 1] - g.rowptr[c];
+    if (deg > 31) deg = 31;  // lane 0 is the site itself; slot 31 (degree 32) handled below
+    present = (1u << deg) - 1u;
+  }
+  const bool active = lane == 0 || ((present >> (lane - 1)) & 1u);
+  if (active) {
+    const uint32_t cand = lane == 0 ? c : f_slot_site(X, c, (uint32_t)lane - 1u);
+    const double old = X.lvl[0][cand];  // in flight together with the gather
+    FHood h;
+    f_gather(X, cand, h);
+    double b;
+    const double p = f_rate(X, h, f_adm_mask(X, h), b);
+    if (p != old) {
+      X.lvl[0][cand] = p;
+      const double delta = p - old;
+      uint32_t i = cand;
+      for (int k = 1; k <= X.top; ++k) {
+        i >>= 5;
+        f_tree_add(&X.lvl[k][i], X.A->fast_smem_tree != 0, delta);
+      }
+    }
+  }
+  __syncwarp();
+  if (g.kind != 0 && g.rowptr[c + 1] - g.rowptr[c] == 32) {  // the 32nd neighbour of a degree-32 vertex
+    if (lane == 0) {
+      const uint32_t cand = f_slot_site(X, c, 31);
+      const double old = X.lvl[0][cand];
+      FHood h;
+      f_gather(X, cand, h);
+      double b;
+      const double p = f_rate(X, h, f_adm_mask(X, h), b);
+      if (p != old) {
+        X.lvl[0][cand] = p;
+        uint32_t i = cand;
+        for (int k = 1; k <= X.top; ++k) { i >>= 5; f_tree_add(&X.lvl[k][i], X.A->fast_smem_tree != 0, p - old); }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// warp reduction of one value per lane (fp64)
+__device__ __forceinline__ double f_warp_sum(double v) {
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+
+// upper levels from the leaves (exact re-summation); four rows of 32 children in flight
+__device__ __noinline__ void f_rebuild_upper(const FCtx& X) {
+  for (int k = 1; k <= X.top; ++k) {
+    const uint32_t nk = X.lvl_n[k], nc = X.lvl_n[k - 1];
+    const double* child = X.lvl[k - 1];
+    for (uint32_t i = 0; i < nk; i += 4) {
+      double v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t c = (i + q) * 32u + (uint32_t)X.lane;
+        v[q] = c < nc ? child[c] : 0.0;
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] += __shfl_xor_sync(FULL, v[q], d);
+      }
+      if (X.lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (i + q < nk) X.lvl[k][i + q] = v[q];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// every leaf from the lattice state, then the upper levels
+__device__ __noinline__ void f_rebuild_all(const FCtx& X) {
+  const uint32_t nv = X.A->g.nv;
+  for (uint32_t s = X.lane; s < nv; s += 32) {
+    FHood h;
+    f_gather(X, s, h);
+    double b;
+    X.lvl[0][s] = f_rate(X, h, f_adm_mask(X, h), b);
+  }
+  __syncwarp();
+  f_rebuild_upper(X);
+}
+
+// select the site whose cumulative rate interval contains `target`; resid = offset inside the site.
+// The 32-wide prefix scans run in fp32 (a relative 1e-7 perturbation of the selection probabilities,
+// far below what any ensemble statistic resolves; fp64 adds cost ~6x the latency on this part);
+// the tree itself and the total rate stay fp64.
+__device__ __forceinline__ bool f_select(const FCtx& X, double target64, uint32_t& site, double& resid) {
+  uint32_t idx = 0;
+  float target = (float)target64;
+  for (int k = X.top; k >= 0; --k) {
+    const uint32_t base = idx * 32u;
+    const uint32_t c = base + (uint32_t)X.lane;
+    const double val64 = c < X.lvl_n[k] ? X.lvl[k][c] : 0.0;
+    const float val = (float)val64;
+    float incl = val;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const float o = __shfl_up_sync(FULL, incl, d);
+      if (X.lane >= d) incl += o;
+    }
+    uint32_t m = __ballot_sync(FULL, (incl > target) && (val64 > 0.0));
+    int j;
+    if (m) {
+      j = __ffs(m) - 1;
+    } else {  // rounding pushed the target past the last child: take the last non-empty one
+      m = __ballot_sync(FULL, val64 > 0.0);
+      if (m == 0) return false;  // stale sum over an empty subtree: caller re-sums and retries
+      j = 31 - __clz(m);
+    }
+    const float vj = __shfl_sync(FULL, val, j);
+    const float ej = __shfl_sync(FULL, incl, j) - vj;
+    target -= ej;
+    if (target < 0.0f) target = 0.0f;
+    if (!(target < vj)) target = vj * 0.999999f;
+    idx = base + (uint32_t)j;
+  }
+  site = idx;
+  resid = (double)target;
+  return true;
+}
+
+__device__ __forceinline__ void f_log(const FCtx& X, FRep& r, uint32_t type, uint32_t flags, double time, uint32_t cell,
+                                      uint32_t parent, uint32_t site0, uint32_t site2_1, uint32_t clone, uint32_t label) {
+  if (r.log_on) {
+    const uint32_t c = log_emit(X.A, X.local_idx, X.lane, r.nlog, r.cur_chunk, type, flags, time, cell, parent,
+                                site0 + 1, site2_1, clone, label);
+    if (c == kNone) { r.log_on = false; r.status = JSB_ST_LOG_OVERFLOW; }
+    else r.cur_chunk = c;
+  }
+  r.nlog++;
+}
+
+// remove the cell of clone c on site v (death, displacement, excision)
+__device__ __forceinline__ void f_kill(const FCtx& X, FRep& r, uint32_t v, uint32_t c, double time, uint32_t flags) {
+  const uint32_t cid = X.track_ids ? X.cellid[v] : 0u;
+  __syncwarp();
+  f_log(X, r, JSB_EV_DEATH, flags, time, cid, 0, v, 0, c, 0);
+  if (X.lane == 0) X.clone[v] = 0;
+  __syncwarp();
+  r.wsum -= X.c_alpha[c - 1];
+}
+
+// cell_birth (:320-416 / :419-537) without the rejection test; v divides onto w
+__device__ __forceinline__ bool f_birth(const FCtx& X, FRep& r, uint32_t v, uint32_t w, uint32_t sp, uint32_t occ,
+                                     bool& mutant_stays) {
+  const DevPoint& P = *X.P;
+  mutant_stays = false;
+  uint64_t wa, wb;
+  draw_block_nl(X.key, r.it, 0, DS_DRIVER_COIN, 0, wa, wb);
+  const double rr = u01_53(wa);
+  int child_node = -1;
+  bool driver;
+  if (P.method == JSB_METHOD_TREE) {
+    if (rr <= P.mu) {
+      const int last = (int)X.c_label[sp - 1] - 1;
+      for (int ed = 0; ed < P.n_edges && child_node < 0; ++ed) {
+        if (X.edge_parent[ed] != last) continue;
+        const int cand = X.edge_child[ed];
+        bool present = false;
+        for (uint32_t s0 = X.lane; s0 < r.S; s0 += 32)
+          if (X.c_parent[s0] == sp && (int)X.c_label[s0] - 1 == cand) present = true;
+        present = __any_sync(FULL, present);
+        if (!present) child_node = cand;
+      }
+    }
+    driver = child_node >= 0;
+  } else {
+    driver = !(rr > P.mu);
+  }
+  if (driver && r.S >= (uint32_t)kMaxClones) { r.status = JSB_ST_CLONE_CAPACITY; return false; }
+  uint32_t first_flag = JSB_EVF_GROUP_START;
+  if (occ != 0) {
+    f_kill(X, r, w, occ, r.t, JSB_EVF_DISPLACED | first_flag);
+    first_flag = 0;
+    r.n_disp++;
+    r.n -= 1;
+  }
+  const uint32_t nid = r.next_id, nid2 = r.next_id + 1;
+  r.next_id += 2;
+  const uint32_t parent = X.track_ids ? X.cellid[v] : 0u;
+  __syncwarp();
+  if (!driver) {
+    f_log(X, r, JSB_EV_DUPLICATE, first_flag, r.t, nid, parent, v, 0, sp, 0);
+    f_log(X, r, JSB_EV_DUPLICATE, 0, r.t, nid2, parent, w, 0, sp, 0);
+    if (X.lane == 0) {
+      if (X.track_ids) { X.cellid[v] = nid; X.cellid[w] = nid2; }
+      X.clone[w] = (uint16_t)sp;
+    }
+    r.wsum += X.c_alpha[sp - 1];
+  } else {
+    uint32_t label;
+    double nalpha;
+    if (P.method == JSB_METHOD_TREE) {
+      label = (uint32_t)child_node + 1;
+      nalpha = X.node_rate[child_node];
+    } else {
+      uint64_t a, b;
+      draw_block_nl(X.key, r.it, 0, DS_LABEL, 0, a, b);
+      const uint32_t j = bounded(X.key, a, 1000u - r.S, r.it, DS_LABEL, 0, 0);
+      label = pick_label(r.used_w, j, X.lane);
+      if ((uint32_t)X.lane == (label >> 5)) r.used_w |= 1u << (label & 31u);
+      nalpha = X.c_alpha[sp - 1] + fabs(P.adv_mean + P.adv_std * contract_randn(X.key, r.it));
+    }
+    const uint32_t nsp = r.S + 1;
+    const bool coin = u01_53(wb) < 0.5;
+    f_log(X, r, JSB_EV_MUTATION, first_flag, r.t, nid2, parent, coin ? w : v, 0, nsp, label);
+    f_log(X, r, JSB_EV_DUPLICATE, 0, r.t, nid, parent, coin ? v : w, 0, sp, 0);
+    if (X.lane == 0) {
+      X.c_alpha[r.S] = nalpha;
+      X.c_parent[r.S] = (uint16_t)sp;
+      X.c_label[r.S] = (uint16_t)label;
+      if (coin) {  // mutant on the new site
+        if (X.track_ids) { X.cellid[v] = nid; X.cellid[w] = nid2; }
+        X.clone[w] = (uint16_t)nsp;
+      } else {     // mutant stays, the wild-type daughter moves out
+        if (X.track_ids) { X.cellid[w] = nid; X.cellid[v] = nid2; }
+        X.clone[w] = (uint16_t)sp;
+        X.clone[v] = (uint16_t)nsp;
+      }
+    }
+    mutant_stays = !coin;
+    r.S = nsp;
+    r.wsum += nalpha;
+  }
+  __syncwarp();
+  r.n += 1;
+  r.n_births++;
+  return true;
+}
+
+// excision: k = trunc(n·ratio) cells uniformly without replacement, deaths logged at tb (:813-838)
+__device__ __noinline__ void f_excision(const FCtx& X, FRep& r, double tb, double ratio) {
+  const uint32_t nv = X.A->g.nv;
+  const int lane = X.lane;
+  long long kk = (long long)trunc((double)r.n * ratio);
+  if (kk < 0) kk = 0;
+  if (kk > (long long)r.n) kk = (long long)r.n;
+  const uint32_t k = (uint32_t)kk;
+  // alive sites, ascending, into inds[]
+  uint32_t cnt = 0;
+  for (uint32_t base = 0; base < nv; base += 32) {
+    const uint32_t s = base + lane;
+    const bool alive = s < nv && X.clone[s] != 0;
+    const uint32_t m = __ballot_sync(FULL, alive);
+    if (alive) X.inds[cnt + __popc(m & ((1u << lane) - 1u))] = s;
+    cnt += __popc(m);
+  }
+  __syncwarp();
+  // partial Fisher-Yates: k uniform draws without replacement
+  for (uint32_t base = 0; base < k; base += 32) {
+    const uint32_t i = base + lane;
+    uint32_t jm = 0;
+    if (i < k) {
+      uint64_t a, b;
+      draw_block(X.key, r.it, 0, DS_EXCISION, i, a, b);
+      jm = i + bounded(X.key, a, cnt - i, r.it, DS_EXCISION, i, 0);
+    }
+    const uint32_t c2 = (k - base) < 32u ? (k - base) : 32u;
+    for (uint32_t l = 0; l < c2; ++l) {
+      const uint32_t j = __shfl_sync(FULL, jm, (int)l);
+      if (lane == 0) {
+        const uint32_t ii = base + l;
+        const uint32_t tj = X.inds[j], ti = X.inds[ii];
+        X.inds[j] = ti;
+        X.inds[ii] = tj;
+      }
+    }
+    __syncwarp();
+  }
+  for (uint32_t i = 0; i < k; ++i)
+    f_kill(X, r, X.inds[i], (uint32_t)X.clone[X.inds[i]], tb, JSB_EVF_EXCISION | (i == 0 ? JSB_EVF_GROUP_START : 0));
+  r.n -= k;
+  r.n_exc += k;
+  __syncwarp();
+  f_rebuild_all(X);
+  r.since_rebuild = 0;
+}
+
+__device__ __noinline__ void f_seed(const FCtx& X, FRep& r) {
+  const DevPoint& P = *X.P;
+  const DevGraph& g = X.A->g;
+  const int lane = X.lane;
+  for (uint32_t i = lane; i < (g.nv + 1) / 2; i += 32) reinterpret_cast<uint32_t*>(X.clone)[i] = 0;
+  for (uint32_t i = lane; i < g.nv; i += 32) X.lvl[0][i] = 0.0;
+  for (int k = 1; k <= X.top; ++k)
+    for (uint32_t i = lane; i < X.lvl_n[k]; i += 32) X.lvl[k][i] = 0.0;
+  __syncwarp();
+  uint32_t n0 = 0;
+  if (P.n_start == 1) {
+    if (X.A->n_cand > 0) {
+      uint32_t j = 0;
+      if (X.A->n_cand > 1) {
+        uint64_t a, b;
+        draw_block_nl(X.key, 0, 0, DS_SEED_TIE, 0, a, b);
+        j = bounded(X.key, a, X.A->n_cand, 0, DS_SEED_TIE, 0, 0);
+      }
+      const uint32_t v0 = X.A->seed_cand[j];
+      if (lane == 0) { X.clone[v0] = 1; if (X.track_ids) X.cellid[v0] = 1; }
+      n0 = 1;
+    }
+  } else if (P.n_start > 1) {
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int i = 0; i < P.n_start; ++i) {
+        uint64_t a, b;
+        draw_block_nl(X.key, 0, 0, DS_SEED_POS, (uint32_t)i, a, b);
+        uint32_t pos = bounded(X.key, a, g.nv - (uint32_t)i, 0, DS_SEED_POS, (uint32_t)i, 0);
+        uint32_t ins = 0;
+        for (uint32_t q = 0; q < cnt; ++q)
+          if (X.samp[q] <= pos) { ++pos; ins = q + 1; }
+        for (uint32_t q = cnt; q > ins; --q) X.samp[q] = X.samp[q - 1];
+        X.samp[ins] = pos;
+        ++cnt;
+        X.clone[pos] = 1;
+        if (X.track_ids) X.cellid[pos] = (uint32_t)i + 1;
+      }
+    }
+    n0 = (uint32_t)P.n_start;
+  }
+  __syncwarp();
+  const double a0 = (P.method == JSB_METHOD_TREE) ? P.root_rate : P.rate_birth;
+  if (lane == 0) {
+    X.c_alpha[0] = a0;
+    X.c_parent[0] = 0;
+    X.c_label[0] = (P.method == JSB_METHOD_TREE) ? (uint16_t)(P.root_node + 1) : (uint16_t)1;
+  }
+  __syncwarp();
+  r.n = n0;
+  r.next_id = n0 + 1;
+  r.S = n0 > 0 ? 1 : 0;
+  r.wsum = a0 * (double)n0;
+  r.used_w = 0;
+  if (lane == 0) r.used_w = 0x3u;
+  if (lane == 31) r.used_w = 0xFFFFFE00u;
+  if (n0 > 0) f_rebuild_all(X);
+  r.since_rebuild = 0;
+}
+
+__device__ __noinline__ void f_outputs(const FCtx& X, const FRep& r) {
+  const RunArgs& A = *X.A;
+  const int lane = X.lane;
+  const uint32_t nv = A.g.nv;
+  __syncwarp();
+  if (lane == 0) {
+    jsb_summary s;
+    s.n_iterations = (uint64_t)r.n_births + r.n_deaths + r.n_migr;  // state-changing events only
+    s.n_events = r.nlog;
+    s.t_final = r.t;
+    s.n_effective = r.n_births + r.n_deaths + r.n_migr + (r.n_exc ? 1u : 0u);
+    s.n_births = r.n_births;
+    s.n_deaths = r.n_deaths;
+    s.n_migrations = r.n_migr;
+    s.n_displaced = r.n_disp;
+    s.n_excised = r.n_exc;
+    s.n_alive = r.n;
+    s.n_clones = r.S;
+    s.next_cell_id = r.next_id;
+    s.status = r.status;
+    A.summaries[X.local_idx] = s;
+  }
+  // clone sizes are not tracked during the run: count them on the final lattice
+  for (uint32_t i = lane; i < r.S; i += 32) X.c_cnt[i] = 0;
+  __syncwarp();
+  for (uint32_t v = lane; v < nv; v += 32) {
+    const uint32_t cl = X.clone[v];
+    if (cl) atomicAdd(&X.c_cnt[cl - 1], 1u);
+  }
+  __syncwarp();
+  long long off = -1;
+  if (A.clone_pool) {
+    unsigned long long o = 0;
+    if (lane == 0) o = atomicAdd(A.clone_pool_next, (unsigned long long)r.S);
+    o = __shfl_sync(FULL, o, 0);
+    if (o + r.S <= A.clone_pool_cap) {
+      off = (long long)o;
+      for (uint32_t i = lane; i < r.S; i += 32) {
+        jsb_clone c;
+        c.alpha = X.c_alpha[i];
+        c.count = X.c_cnt[i];
+        c.parent = X.c_parent[i];
+        c.label = X.c_label[i];
+        A.clone_pool[o + i] = c;
+      }
+    }
+    if (lane == 0) A.clone_off[X.local_idx] = off;
+  }
+  if (A.out_clone) {
+    uint16_t* oc = A.out_clone + (size_t)X.local_idx * nv;
+    uint32_t* oi = A.out_cell + (size_t)X.local_idx * nv;
+    for (uint32_t v = lane; v < nv; v += 32) {
+      const uint16_t cl = X.clone[v];
+      oc[v] = cl;
+      oi[v] = cl ? X.cellid[v] : 0u;
+    }
+  }
+  __syncwarp();
+}
+
+// apply the state-changing event that fires on site v (resid = offset inside v's rate interval)
+__device__ __forceinline__ bool f_event(const FCtx& X, FRep& r, uint32_t v, double resid, uint64_t w_nbr) {
+  const DevPoint& P = *X.P;
+  const int lane = X.lane;
+  FHood h;
+  f_gather(X, v, h);  // one round trip: the site and its whole neighbourhood
+  const uint32_t c = h.own;
+  const uint32_t adm_mask = f_adm_mask(X, h);
+  double bpart;
+  f_rate(X, h, adm_mask, bpart);
+  int kind = resid < bpart ? 0 : (resid < bpart + P.rate_death ? 1 : 2);  // birth | death | migration
+  if (kind == 0 && adm_mask == 0) kind = 1;  // rounding at a part boundary
+  if (kind == 2 && h.empty == 0) kind = 1;
+  bool ok = true;
+  if (kind == 1) {  // cell_death :574-586
+    f_kill(X, r, v, c, r.t, JSB_EVF_GROUP_START);
+    r.n -= 1;
+    r.n_deaths++;
+    f_refresh_around(X, v);
+  } else {
+    const uint32_t pool = kind == 0 ? adm_mask : h.empty;
+    const uint32_t want = bounded(X.key, w_nbr, (uint32_t)__popc(pool), r.it, DS_F_KIND_NBR, 0, 1);
+    uint32_t m = pool;
+    for (uint32_t q = 0; q < want; ++q) m &= m - 1;  // the want-th admissible / empty neighbour
+    const uint32_t slot = (uint32_t)__ffs(m) - 1u;
+    const uint32_t w = f_slot_site(X, v, slot);
+    if (kind == 0) {
+      uint32_t occ = 0;
+      if (X.A->g.kind == 0) {
+#pragma unroll
+        for (int b = 0; b < 6; ++b)
+          if ((uint32_t)b == slot) occ = h.cw[b];
+      } else {
+        occ = h.cwl[slot];
+      }
+      bool mutant_stays;
+      ok = f_birth(X, r, v, w, c, occ, mutant_stays);
+      if (ok) {
+        f_refresh_around(X, w);
+        if (mutant_stays) f_refresh_around(X, v);
+      }
+    } else {  // migration_cell :592-613
+      const uint32_t cid = X.track_ids ? X.cellid[v] : 0u;
+      __syncwarp();
+      if (lane == 0) {
+        X.clone[w] = (uint16_t)c;
+        X.clone[v] = 0;
+        if (X.track_ids) X.cellid[w] = cid;
+      }
+      __syncwarp();
+      f_log(X, r, JSB_EV_MIGRATION, JSB_EVF_GROUP_START, r.t, cid, 0, w, v + 1, c, 0);
+      r.n_migr++;
+      f_refresh_around(X, v);
+      f_refresh_around(X, w);
+    }
+  }
+  r.since_rebuild++;
+  return ok;
+}
+
+// time of the null iteration that crosses tau: first point of a rate-nu process after tau,
+// conditioned to fall before t_new
+__device__ __forceinline__ double f_null_crossing(double tau, double t_new, double nu, double u) {
+  if (!(nu > 0.0)) return tau;
+  const double x = tau + (-log1p(-u * (1.0 - exp(-nu * (t_new - tau))))) / nu;
+  return x < t_new ? x : tau;
+}
+
+__device__ __forceinline__ void f_run(const FCtx& X) {
+  const RunArgs& A = *X.A;
+  const DevPoint& P = *X.P;
+  const int lane = X.lane;
+  const uint32_t nv = A.g.nv;
+  const bool intent = (P.quirks & JSB_QUIRK_EXCISION_INTENT) != 0;
+  const double dm = P.rate_death + P.rate_migration;
+  FRep r;
+  r.t = 0.0; r.wsum = 0.0; r.it = 0; r.nlog = 0; r.cur_chunk = 0;
+  // which excision entry can fire: the reference's method 1 never advances its index (only entry 1),
+  // method 2 advances it every iteration (in effect only the last entry); intent: one after another
+  r.bott_id = P.n_bott > 0 ? ((intent || P.method != JSB_METHOD_TREE) ? 1 : P.n_bott) : 0;
+  r.snap_idx = 0;
+  r.status = JSB_ST_OK;
+  r.n_births = r.n_deaths = r.n_migr = r.n_disp = r.n_exc = 0;
+  r.log_on = (A.flags & JSB_OUT_EVENTS) != 0;
+  { FCtx xc = X; FRep rc = r; f_seed(xc, rc); r = rc; }
+
+#ifdef JSB_PROFILE
+  long long fp[6] = {0, 0, 0, 0, 0, 0}, ft0 = clock64();
+#define FPROF(i) do { long long _t = clock64(); fp[i] += _t - ft0; ft0 = _t; } while (0)
+#else
+#define FPROF(i)
+#endif
+  while (r.t < P.Tf && r.n > 0) {  // loop test :687
+    if (P.max_iter && r.it >= P.max_iter) { r.status = JSB_ST_MAX_ITER; break; }
+    FPROF(5);
+    if (r.since_rebuild >= kFastRebuild) { FCtx xc = X; f_rebuild_upper(xc); r.since_rebuild = 0; }
+    FPROF(0);
+    const double Lam = f_warp_sum((uint32_t)lane < X.lvl_n[X.top] ? X.lvl[X.top][lane] : 0.0);
+    if (!(Lam > 0.0)) {  // nothing can change any more: the reference idles through null events to Tf
+      r.t = P.Tf;
+      break;
+    }
+    r.it += 1;
+    uint64_t wa, wb, wc, wd;
+    draw_block(X.key, r.it, 0, DS_F_TIME_SELECT, 0, wa, wb);
+    draw_block(X.key, r.it, 0, DS_F_KIND_NBR, 0, wc, wd);
+    const double t_new = r.t + (-contract_log(u01_open(wa))) / Lam;
+    const double nu = fmax(r.wsum + dm * (double)r.n - Lam, 0.0);  // rate of the reference's null iterations
+    FPROF(1);
+
+    // an excision time inside (t, t_new]?
+    bool excise_after = false;
+    double tbv = 0.0, ratio = 0.0;
+    int next_bott = r.bott_id;
+    if (r.bott_id > 0) {
+      tbv = X.tb[r.bott_id - 1];
+      if (tbv > r.t && tbv <= t_new) {
+        ratio = X.ratio[r.bott_id - 1];
+        next_bott = intent ? ((r.bott_id < P.n_bott) ? r.bott_id + 1 : 0) : 0;
+        uint64_t we, wf;
+        draw_block_nl(X.key, r.it, 0, DS_F_BOUNDARY, 0, we, wf);
+        if (u01_53(we) < exp(-nu * (t_new - tbv))) {
+          excise_after = true;  // the event itself is the iteration that crosses tb: event, then excision
+        } else {
+          // a null iteration crosses tb: excision on the current state; the clock restarts there
+          r.t = f_null_crossing(tbv, t_new, nu, u01_53(wf));
+          r.bott_id = next_bott;
+          { FCtx xc = X; FRep rc = r; f_excision(xc, rc, tbv, ratio); r = rc; }
+          continue;
+        }
+      }
+    }
+    // Tf inside (t, t_new]: the event happens only if it is the iteration that crosses Tf
+    if (!excise_after && !(t_new < P.Tf)) {
+      uint64_t we, wf;
+      draw_block_nl(X.key, r.it, 0, DS_F_BOUNDARY, 1, we, wf);
+      if (!(u01_53(we) < exp(-nu * (t_new - P.Tf)))) {
+        r.t = f_null_crossing(P.Tf, t_new, nu, u01_53(wf));
+        if (r.t < P.Tf) r.t = P.Tf;
+        break;
+      }
+    }
+    // snapshots are taken before the event of the crossing iteration (:708-714)
+    while (r.snap_idx < P.n_snap && t_new > X.tsnap[r.snap_idx]) {
+      if (lane == 0 && A.snaps) {
+        jsb_snapshot s;
+        s.time = t_new; s.iteration = r.it; s.n_events_before = r.nlog; s.n_alive = r.n;
+        s.index = (uint32_t)r.snap_idx;
+        A.snaps[(size_t)X.local_idx * A.max_snap + r.snap_idx] = s;
+      }
+      r.snap_idx++;
+    }
+    uint32_t v;
+    double resid;
+    if (!f_select(X, u01_53(wb) * Lam, v, resid)) {  // stale sums over an emptied subtree: re-sum, retry
+      { FCtx xc = X; f_rebuild_upper(xc); }
+      r.since_rebuild = 0;
+      continue;  // (r.it moved on: the retry uses fresh draws; a pending excision is decided again)
+    }
+    FPROF(2);
+    r.t = t_new;
+    if (!f_event(X, r, v, resid, wd)) break;
+    FPROF(3);
+    if (excise_after) {
+      r.bott_id = next_bott;
+      { FCtx xc = X; FRep rc = r; f_excision(xc, rc, tbv, ratio); r = rc; }
+    }
+    (void)wc;
+  }
+#ifdef JSB_PROFILE
+  if (lane == 0 && (X.local_idx < 2 || r.n_births > 60000))
+    printf("fast rep %lld events %u S %u n %u | rebuild %lld draws %lld select %lld event %lld other %lld\n", (long long)X.local_idx,
+           r.n_births + r.n_deaths + r.n_migr, r.S, r.n, fp[0], fp[1], fp[2], fp[3], fp[5]);
+#endif
+  if (r.status == JSB_ST_OK && P.rate_death == 0.0 && r.n == nv && !(r.t < P.Tf)) r.status = JSB_ST_NONTERMINATING;
+  { FCtx xc = X; FRep rc = r; f_outputs(xc, rc); }
+}
+
+__global__ void __launch_bounds__(384, 1) fast_kernel(const __grid_constant__ RunArgs A) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const uint64_t slot = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  const WsLayout& L = A.L;
+  uint8_t* base = A.ws + slot * A.ws_stride;
+  unsigned char* sw = s_dyn + (size_t)warp * A.smem_per_warp;
+  FCtx X;
+  X.A = &A;
+  X.lane = lane;
+  X.clone = reinterpret_cast<uint16_t*>(base + L.clone);
+  X.cellid = reinterpret_cast<uint32_t*>(base + L.cellid);
+  X.inds = reinterpret_cast<uint32_t*>(base + L.inds);
+  X.samp = reinterpret_cast<uint32_t*>(base + L.samp);
+  X.c_cnt = reinterpret_cast<uint32_t*>(base + L.c_len);
+  X.c_parent = reinterpret_cast<uint16_t*>(base + L.c_parent);
+  X.c_label = reinterpret_cast<uint16_t*>(base + L.c_label);
+  DevPoint* sP = reinterpret_cast<DevPoint*>(sw);
+  constexpr size_t kFastFixed = ((sizeof(DevPoint) + 15) & ~size_t(15)) + sizeof(double) * kTab;
+  X.c_alpha = reinterpret_cast<double*>(sw + ((sizeof(DevPoint) + 15) & ~size_t(15)));  // α per clone: shared
+  // tree levels: leaves in the (otherwise unused) list arena, upper levels in shared memory when they fit
+  X.lvl[0] = reinterpret_cast<double*>(base + L.arena);
+  X.lvl_n[0] = A.g.nv;
+  double* up = A.fast_smem_tree ? reinterpret_cast<double*>(sw + kFastFixed)
+                                : reinterpret_cast<double*>(base + L.ftree);
+  int k = 0;
+  while (X.lvl_n[k] > 32 && k + 1 < kFastLevels) {
+    X.lvl_n[k + 1] = (X.lvl_n[k] + 31) / 32;
+    X.lvl[k + 1] = up;
+    up += X.lvl_n[k + 1];
+    ++k;
+  }
+  X.top = k;
+  for (int q = k + 1; q < kFastLevels; ++q) { X.lvl[q] = nullptr; X.lvl_n[q] = 0; }
+  X.key.k0 = (uint32_t)A.seed ^ 0xFA57FA57u;  // a stream family of its own
+  X.key.k1 = (uint32_t)(A.seed >> 32);
+  X.track_ids = (A.flags & (JSB_OUT_EVENTS | JSB_OUT_LATTICE)) != 0;
+
+  for (;;) {
+    unsigned long long idx = 0;
+    if (lane == 0) idx = atomicAdd(A.work_counter, 1ull);
+    idx = __shfl_sync(FULL, idx, 0);
+    if ((long long)idx >= A.n_local) break;
+    const int64_t gidx = A.g_begin + (int64_t)idx;
+    X.local_idx = (int64_t)idx;
+    X.key.stream = (uint32_t)gidx;
+    {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(A.points + (gidx / A.reps_per_point));
+      uint32_t* dst = reinterpret_cast<uint32_t*>(sP);
+      __syncwarp();
+      for (uint32_t i = lane; i < sizeof(DevPoint) / 4; i += 32) dst[i] = src[i];
+      __syncwarp();
+    }
+    const DevPoint* P = sP;
+    X.P = P;
+    X.tb = A.dpool + P->bott_off;
+    X.ratio = X.tb + P->n_bott;
+    X.tsnap = A.dpool + P->snap_off;
+    X.node_rate = A.dpool + P->rate_off;
+    X.edge_parent = A.ipool + P->edge_off;
+    X.edge_child = X.edge_parent + P->n_edges;
+    f_run(X);
+  }
+}
+
+static size_t fast_upper_entries(uint32_t nv) {
+  size_t total = 0;
+  uint32_t n = nv;
+  while (n > 32) { n = (n + 31) / 32; total += n; }
+  return total;
+}
+
+int fast_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int max_optin = 0;
+  if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
+  const size_t point_bytes = ((sizeof(DevPoint) + 15) & ~size_t(15)) + sizeof(double) * kTab;  // point + α table
+  const size_t tree_bytes = 8 * fast_upper_entries(args.g.nv);
+  int cap = 12;
+  if (max_warps_per_sm > 0 && max_warps_per_sm < cap) cap = max_warps_per_sm;
+  size_t per_warp = (point_bytes + tree_bytes + 15) & ~size_t(15);
+  bool smem_tree = per_warp * 4 <= (size_t)max_optin;  // at least 4 warps per SM with the tree in smem
+  if (!smem_tree) per_warp = point_bytes;
+  int w = (int)((size_t)max_optin / per_warp);
+  if (w > cap) w = cap;
+  if (w < 1) return -1;
+  args.fast_smem_tree = smem_tree ? 1u : 0u;
+  args.smem_per_warp = (uint32_t)per_warp;
+  if (cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * w)) != cudaSuccess) return -1;
+  *warps_per_block = w;
+  return 0;
+}
+
+int launch_fast(const RunArgs& args, int grid_blocks, int warps_per_block, void* stream) {
+  fast_kernel<<<grid_blocks, warps_per_block * 32, (size_t)args.smem_per_warp * warps_per_block, (cudaStream_t)stream>>>(args);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace jsb

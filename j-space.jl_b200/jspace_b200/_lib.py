@@ -26,6 +26,7 @@ QUIRK_DEBUG_SERIAL = 0x100
 QUIRK_DEBUG_EXACT_CLASSES = 0x200
 QUIRK_DEBUG_WIDE_GUARD = 0x400
 OUT_EVENTS, OUT_LATTICE, OUT_LISTS = 0x1, 0x2, 0x4
+MODE_REJECTION_FREE = 0x100
 EV_DUPLICATE, EV_MUTATION, EV_DEATH, EV_MIGRATION = 0, 1, 2, 3
 EVF_GROUP_START, EVF_DISPLACED, EVF_EXCISION = 0x1, 0x2, 0x4
 ST_OK, ST_NONTERMINATING, ST_CLONE_CAPACITY, ST_LOG_OVERFLOW, ST_MAX_ITER, ST_INTERNAL = range(6)
