@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--reps", type=int, default=0, help="replicates per GPU (default: the workload's 4096)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fast", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -301,6 +302,23 @@ def main():
                "what": "jsb_run with JSB_OUT_EVENTS|JSB_OUT_LATTICE: event logs, final lattices, clone tables and "
                        "summaries of every replicate copied to host memory; host wall clock"}
 
+    # ---- extra: the rejection-free mode on the same ensemble, one pass --------------
+    fast = None
+    if not args.no_fast:
+        barrier()
+        rf = J.run_ensemble(graph, point, total_reps, seed=BASE_SEED, flags=L.MODE_REJECTION_FREE, g_begin=g0,
+                            g_end=g0 + reps, device=local_rank)
+        ft = torch.tensor([rf.kernel_ms], dtype=torch.float64, device="cuda")
+        fe = torch.tensor([float(rf.summaries["n_iterations"].sum())], dtype=torch.float64, device="cuda")
+        launches += rf.launches
+        rf.close()
+        if dist is not None:
+            dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+            dist.all_reduce(fe, op=dist.ReduceOp.SUM)
+        fast = {"replicates_per_s": world * reps / (ft.item() / 1e3), "state_changing_events_per_s": fe.item() / (ft.item() / 1e3),
+                "ms": ft.item(), "note": "JSB_MODE_REJECTION_FREE: same law, null events not simulated; KS-validated, "
+                                         "not event-for-event comparable"}
+
     # ---- CPU baseline (rank 0, N=1 only): oracle port on the host cores, bounded sample --------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -335,6 +353,7 @@ def main():
             "gpu_launches": int(all_launches),
             "clocks": clocks.summary(),
             "ensemble_histogram_n_alive": h.tolist()[:8],
+            "rejection_free_mode": fast,
         }
         print(json.dumps(line))
     if dist is not None:
