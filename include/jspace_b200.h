@@ -62,6 +62,10 @@ extern "C" {
  * identical.                                                                               */
 #define JSB_QUIRK_DEBUG_EXACT_CLASSES 0x200u
 #define JSB_QUIRK_DEBUG_WIDE_GUARD 0x400u
+/* Rejection-free mode test hook: after every event recompute the rates around the changed sites
+ * from scratch and compare with the incrementally maintained tree (status JSB_ST_INTERNAL on a
+ * mismatch).                                                                                 */
+#define JSB_QUIRK_DEBUG_VERIFY_TREE 0x800u
 
 /* ---- output selection (jsb_run_opts.flags) -------------------------------------------- */
 #define JSB_OUT_EVENTS 0x1u  /* keep the per-replicate event log (`df`)                   */

@@ -505,7 +505,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
   if ((opts->flags & JSB_MODE_REJECTION_FREE) && g->kind == 1) {
     uint32_t maxdeg = 0;
     for (int64_t v = 0; v < g->nv; ++v) maxdeg = std::max(maxdeg, g->rowptr[v + 1] - g->rowptr[v]);
-    if (maxdeg > 32) return fail(JSB_ECAPACITY, "JSB_MODE_REJECTION_FREE supports vertex degrees up to 32 (graph has %u)", maxdeg);
+    if (maxdeg > 31) return fail(JSB_ECAPACITY, "JSB_MODE_REJECTION_FREE supports vertex degrees up to 31 (graph has %u)", maxdeg);
   }
   if (g_begin < 0 || g_end > g_total || g_begin > g_end) return fail(JSB_EINVAL, "replicate range [%lld,%lld) is outside [0,%lld)", (long long)g_begin, (long long)g_end, (long long)g_total);
   bool need_closeness = false;

@@ -1816,7 +1816,8 @@ int launch_ssa(const RunArgs& args, int grid_blocks, int warps_per_block, void* 
 // exp(−ν (t' − τ)), ν = λ_reference − Σ p_v being the null-iteration rate.
 // =================================================================================================
 constexpr int kFastLevels = 6;        // 32^6 > 2^28 sites
-constexpr uint32_t kFastRebuild = 2048;
+constexpr uint32_t kFastRebuild = 2048;       // events between re-summations of the upper levels
+constexpr uint32_t kFastRefreshLeaves = 8;   // every this many re-summations the leaves are recomputed too
 enum : uint32_t { DS_F_TIME_SELECT = 12, DS_F_KIND_NBR = 13, DS_F_BOUNDARY = 11 };
 
 struct FCtx {
@@ -1936,8 +1937,8 @@ __device__ __forceinline__ double f_rate(const FCtx& X, const FHood& h, uint32_t
   const uint32_t deg = (uint32_t)__popc(h.present);
   double mpart = 0.0;
   if (deg > 0) {
-    bpart = X.c_alpha[h.own - 1] * (double)__popc(adm_mask) / (double)deg;
-    mpart = X.P->rate_migration * (double)__popc(h.empty) / (double)deg;
+    bpart = (X.c_alpha[h.own - 1] * (double)__popc(adm_mask)) / (double)deg;
+    mpart = (X.P->rate_migration * (double)__popc(h.empty)) / (double)deg;
   }
   return bpart + X.P->rate_death + mpart;
 }
@@ -1948,53 +1949,110 @@ __device__ __forceinline__ void f_tree_add(double* p, bool in_smem, double delta
   else atomicAdd(p, delta);
 }
 
-// site c changed: recompute the rates of c and of all its neighbours (lane 0: c, lane 1+slot: the
-// neighbour in that slot; the candidates of one call are distinct, so no de-duplication is needed)
-__device__ __forceinline__ void f_refresh_around(const FCtx& X, uint32_t c) {
+// Warp-wide view of the neighbourhood of site x: lane = slot (lattice direction / CSR row position,
+// degree <= 31 in this mode), lane 31 = the site itself.  Clones and leaf rates are loaded in ONE
+// round trip.
+struct FWarpHood {
+  uint32_t u;        // neighbour site of this lane's slot
+  uint32_t cu;       // its clone (0 = empty)
+  double leaf;       // its current rate
+  bool present;      // the slot exists
+  uint32_t own;      // clone on x (broadcast)
+  double own_leaf;   // rate of x (broadcast)
+  uint32_t deg;      // degree of x
+};
+
+__device__ __forceinline__ uint32_t f_site_degree(const FCtx& X, uint32_t u) {
+  const DevGraph& g = X.A->g;
+  if (g.kind == 0) return (uint32_t)__popc(lattice_mask(g, u));
+  return g.rowptr[u + 1] - g.rowptr[u];
+}
+
+__device__ __forceinline__ FWarpHood f_warp_gather(const FCtx& X, uint32_t x) {
   const DevGraph& g = X.A->g;
   const int lane = X.lane;
-  uint32_t present;
-  if (g.kind == 0) present = lattice_mask(g, c);
-  else {
-    uint32_t deg = g.rowptr[c + 1] - g.rowptr[c];
-    if (deg > 31) deg = 31;  // lane 0 is the site itself; slot 31 (degree 32) handled below
-    present = (1u << deg) - 1u;
+  FWarpHood h;
+  h.u = x;
+  h.cu = 0;
+  h.leaf = 0.0;
+  if (g.kind == 0) {
+    const uint32_t mask = lattice_mask(g, x);
+    h.present = lane < 6 && ((mask >> lane) & 1u);
+    h.u = f_slot_site(X, x, (uint32_t)lane < 6u ? (uint32_t)lane : 0u);
+  } else {
+    const uint32_t row0 = g.rowptr[x], deg = g.rowptr[x + 1] - row0;
+    h.present = (uint32_t)lane < deg && lane < 31;
+    if (h.present) h.u = g.colidx[row0 + lane];
   }
-  const bool active = lane == 0 || ((present >> (lane - 1)) & 1u);
-  if (active) {
-    const uint32_t cand = lane == 0 ? c : f_slot_site(X, c, (uint32_t)lane - 1u);
-    const double old = X.lvl[0][cand];  // in flight together with the gather
-    FHood h;
-    f_gather(X, cand, h);
-    double b;
-    const double p = f_rate(X, h, f_adm_mask(X, h), b);
-    if (p != old) {
-      X.lvl[0][cand] = p;
-      const double delta = p - old;
-      uint32_t i = cand;
-      for (int k = 1; k <= X.top; ++k) {
-        i >>= 5;
-        f_tree_add(&X.lvl[k][i], X.A->fast_smem_tree != 0, delta);
-      }
+  uint32_t c = 0;
+  double lf = 0.0;
+  if (h.present) { c = X.clone[h.u]; lf = X.lvl[0][h.u]; }
+  if (lane == 31) { c = X.clone[x]; lf = X.lvl[0][x]; }
+  h.own = __shfl_sync(FULL, c, 31);
+  h.own_leaf = __shfl_sync(FULL, lf, 31);
+  if (h.present) { h.cu = c; h.leaf = lf; }
+  h.deg = (uint32_t)__popc(__ballot_sync(FULL, h.present));
+  return h;
+}
+
+// add `delta` to every ancestor of site s
+__device__ __forceinline__ void f_push_up(const FCtx& X, uint32_t s, double delta) {
+  const bool in_smem = X.A->fast_smem_tree != 0;
+  uint32_t i = s;
+#pragma unroll
+  for (int k = 1; k < kFastLevels; ++k) {
+    if (k <= X.top) {
+      i >>= 5;
+      f_tree_add(&X.lvl[k][i], in_smem, delta);
     }
+  }
+}
+
+// The clone on site x changed from a to b (0 = empty); clone[x] == b is already stored and h is a
+// fresh gather of x's neighbourhood.  Each occupied neighbour u moves by
+//     Δp_u = (α_u·(A(c_u,b) − A(c_u,a)) + m·([b=0] − [a=0])) / deg_u
+// (one lane per neighbour, no further loads), x itself is recomputed from the gathered clones.
+__device__ __forceinline__ void f_apply_change(const FCtx& X, uint32_t x, uint32_t a, uint32_t b, const FWarpHood& h) {
+  const int lane = X.lane;
+  const double mig = X.P->rate_migration;
+  if (h.present && h.cu != 0) {
+    const int dadm = (int)f_admissible(X, h.cu, b) - (int)f_admissible(X, h.cu, a);
+    const int demp = (int)(b == 0) - (int)(a == 0);
+    if (dadm != 0 || demp != 0) {
+      const double delta = (X.c_alpha[h.cu - 1] * (double)dadm + mig * (double)demp) / (double)f_site_degree(X, h.u);
+      X.lvl[0][h.u] = h.leaf + delta;
+      f_push_up(X, h.u, delta);
+    }
+  }
+  const uint32_t emp = (uint32_t)__popc(__ballot_sync(FULL, h.present && h.cu == 0));
+  const uint32_t adm = (uint32_t)__popc(__ballot_sync(FULL, h.present && b != 0 && f_admissible(X, b, h.cu)));
+  if (lane == 31) {
+    double p = 0.0;
+    if (b != 0) {
+      p = X.P->rate_death;
+      if (h.deg > 0) p = (X.c_alpha[b - 1] * (double)adm) / (double)h.deg + X.P->rate_death + (mig * (double)emp) / (double)h.deg;
+    }
+    X.lvl[0][x] = p;
+    const double delta = p - h.own_leaf;
+    if (delta != 0.0) f_push_up(X, x, delta);
   }
   __syncwarp();
-  if (g.kind != 0 && g.rowptr[c + 1] - g.rowptr[c] == 32) {  // the 32nd neighbour of a degree-32 vertex
-    if (lane == 0) {
-      const uint32_t cand = f_slot_site(X, c, 31);
-      const double old = X.lvl[0][cand];
-      FHood h;
-      f_gather(X, cand, h);
-      double b;
-      const double p = f_rate(X, h, f_adm_mask(X, h), b);
-      if (p != old) {
-        X.lvl[0][cand] = p;
-        uint32_t i = cand;
-        for (int k = 1; k <= X.top; ++k) { i >>= 5; f_tree_add(&X.lvl[k][i], X.A->fast_smem_tree != 0, p - old); }
-      }
-    }
-    __syncwarp();
+}
+
+// debug (JSB_QUIRK_DEBUG_VERIFY_TREE): every leaf around x must equal the rate recomputed from scratch
+__device__ __noinline__ bool f_verify_around(const FCtx& X, uint32_t x) {
+  const FWarpHood h = f_warp_gather(X, x);
+  bool bad = false;
+  if (h.present || X.lane == 31) {
+    const uint32_t s = X.lane == 31 ? x : h.u;
+    FHood hh;
+    f_gather(X, s, hh);
+    double bp;
+    const double want = f_rate(X, hh, f_adm_mask(X, hh), bp);
+    const double have = X.lvl[0][s];
+    bad = fabs(want - have) > 1e-9 * (1.0 + fabs(want));
   }
+  return __any_sync(FULL, bad);
 }
 
 // warp reduction of one value per lane (fp64)
@@ -2050,7 +2108,9 @@ __device__ __noinline__ void f_rebuild_all(const FCtx& X) {
 __device__ __forceinline__ bool f_select(const FCtx& X, double target64, uint32_t& site, double& resid) {
   uint32_t idx = 0;
   float target = (float)target64;
-  for (int k = X.top; k >= 0; --k) {
+#pragma unroll
+  for (int k = kFastLevels - 1; k >= 0; --k) {
+    if (k > X.top) continue;
     const uint32_t base = idx * 32u;
     const uint32_t c = base + (uint32_t)X.lane;
     const double val64 = c < X.lvl_n[k] ? X.lvl[k][c] : 0.0;
@@ -2363,59 +2423,70 @@ __device__ __noinline__ void f_outputs(const FCtx& X, const FRep& r) {
 __device__ __forceinline__ bool f_event(const FCtx& X, FRep& r, uint32_t v, double resid, uint64_t w_nbr) {
   const DevPoint& P = *X.P;
   const int lane = X.lane;
-  FHood h;
-  f_gather(X, v, h);  // one round trip: the site and its whole neighbourhood
-  const uint32_t c = h.own;
-  const uint32_t adm_mask = f_adm_mask(X, h);
-  double bpart;
-  f_rate(X, h, adm_mask, bpart);
+  const FWarpHood hv = f_warp_gather(X, v);  // round trip: v, its neighbours, their rates
+  const uint32_t c = hv.own;
+  const uint32_t emp_mask = __ballot_sync(FULL, hv.present && hv.cu == 0);
+  const uint32_t adm_mask = __ballot_sync(FULL, hv.present && f_admissible(X, c, hv.cu));
+  const double bpart = hv.deg ? (X.c_alpha[c - 1] * (double)__popc(adm_mask)) / (double)hv.deg : 0.0;
   int kind = resid < bpart ? 0 : (resid < bpart + P.rate_death ? 1 : 2);  // birth | death | migration
   if (kind == 0 && adm_mask == 0) kind = 1;  // rounding at a part boundary
-  if (kind == 2 && h.empty == 0) kind = 1;
+  if (kind == 2 && emp_mask == 0) kind = 1;
   bool ok = true;
+  uint32_t w = v;
   if (kind == 1) {  // cell_death :574-586
     f_kill(X, r, v, c, r.t, JSB_EVF_GROUP_START);
     r.n -= 1;
     r.n_deaths++;
-    f_refresh_around(X, v);
+    f_apply_change(X, v, c, 0, hv);
   } else {
-    const uint32_t pool = kind == 0 ? adm_mask : h.empty;
+    const uint32_t pool = kind == 0 ? adm_mask : emp_mask;
     const uint32_t want = bounded(X.key, w_nbr, (uint32_t)__popc(pool), r.it, DS_F_KIND_NBR, 0, 1);
     uint32_t m = pool;
     for (uint32_t q = 0; q < want; ++q) m &= m - 1;  // the want-th admissible / empty neighbour
-    const uint32_t slot = (uint32_t)__ffs(m) - 1u;
-    const uint32_t w = f_slot_site(X, v, slot);
+    const int slot = __ffs(m) - 1;
+    w = __shfl_sync(FULL, hv.u, slot);
+    const uint32_t occ = __shfl_sync(FULL, hv.cu, slot);
     if (kind == 0) {
-      uint32_t occ = 0;
-      if (X.A->g.kind == 0) {
-#pragma unroll
-        for (int b = 0; b < 6; ++b)
-          if ((uint32_t)b == slot) occ = h.cw[b];
-      } else {
-        occ = h.cwl[slot];
-      }
       bool mutant_stays;
-      ok = f_birth(X, r, v, w, c, occ, mutant_stays);
+      ok = f_birth(X, r, v, w, c, occ, mutant_stays);  // stores the new clones of w (and v)
       if (ok) {
-        f_refresh_around(X, w);
-        if (mutant_stays) f_refresh_around(X, v);
+        // w: occ -> its new clone.  If the mutant stayed on v, v still counts as clone c here and
+        // changes in a second step, against a fresh gather (w has changed meanwhile).
+        const uint32_t cw_new = X.clone[w];
+        const uint32_t cv_new = mutant_stays ? (uint32_t)X.clone[v] : c;
+        if (mutant_stays && lane == 0) X.clone[v] = (uint16_t)c;
+        __syncwarp();
+        const FWarpHood hw = f_warp_gather(X, w);
+        f_apply_change(X, w, occ, cw_new, hw);
+        if (mutant_stays) {
+          if (lane == 0) X.clone[v] = (uint16_t)cv_new;
+          __syncwarp();
+          const FWarpHood hv2 = f_warp_gather(X, v);
+          f_apply_change(X, v, c, cv_new, hv2);
+        }
       }
     } else {  // migration_cell :592-613
       const uint32_t cid = X.track_ids ? X.cellid[v] : 0u;
       __syncwarp();
+      if (lane == 0) X.clone[v] = 0;
+      __syncwarp();
+      f_apply_change(X, v, c, 0, hv);  // w is empty in hv: untouched by this step
       if (lane == 0) {
         X.clone[w] = (uint16_t)c;
-        X.clone[v] = 0;
         if (X.track_ids) X.cellid[w] = cid;
       }
       __syncwarp();
       f_log(X, r, JSB_EV_MIGRATION, JSB_EVF_GROUP_START, r.t, cid, 0, w, v + 1, c, 0);
       r.n_migr++;
-      f_refresh_around(X, v);
-      f_refresh_around(X, w);
+      const FWarpHood hw = f_warp_gather(X, w);
+      f_apply_change(X, w, 0, c, hw);
     }
   }
   r.since_rebuild++;
+  if (ok && (P.quirks & JSB_QUIRK_DEBUG_VERIFY_TREE)) {
+    FCtx xc = X;
+    if (f_verify_around(xc, v) || f_verify_around(xc, w)) { r.status = JSB_ST_INTERNAL; ok = false; }
+  }
   return ok;
 }
 
@@ -2451,10 +2522,15 @@ __device__ __forceinline__ void f_run(const FCtx& X) {
 #else
 #define FPROF(i)
 #endif
+  uint32_t n_resum = 0;
   while (r.t < P.Tf && r.n > 0) {  // loop test :687
     if (P.max_iter && r.it >= P.max_iter) { r.status = JSB_ST_MAX_ITER; break; }
     FPROF(5);
-    if (r.since_rebuild >= kFastRebuild) { FCtx xc = X; f_rebuild_upper(xc); r.since_rebuild = 0; }
+    if (r.since_rebuild >= kFastRebuild) {
+      FCtx xc = X;
+      if (++n_resum % kFastRefreshLeaves == 0) f_rebuild_all(xc); else f_rebuild_upper(xc);
+      r.since_rebuild = 0;
+    }
     FPROF(0);
     const double Lam = f_warp_sum((uint32_t)lane < X.lvl_n[X.top] ? X.lvl[X.top][lane] : 0.0);
     if (!(Lam > 0.0)) {  // nothing can change any more: the reference idles through null events to Tf

@@ -51,6 +51,27 @@ def test_fast_mode_matches_reference_law(jsb, oracle, case):
     assert abs(ext_f - ext_r) < 4 * np.sqrt(ext_r * (1 - ext_r) / n + 1e-9) + 0.02
 
 
+@pytest.mark.parametrize("rule", ["contact", "voter", "hvoter"])
+def test_fast_mode_incremental_tree_is_consistent(jsb, rule):
+    # JSB_QUIRK_DEBUG_VERIFY_TREE: after every event the incrementally updated rates around the
+    # changed sites must equal the rates recomputed from scratch (else status 5)
+    from graphs import random_geometric_csr
+    from jspace_b200 import _lib as L
+    p = jsb.Point(Tf=60.0, rate_birth=0.3, rate_death=0.03, rate_migration=0.05, mu_driver=0.01, rule=rule,
+                  t_bottleneck=[30.0], ratio_bottleneck=[0.4], quirk_flags=L.QUIRK_DEBUG_VERIFY_TREE)
+    for g in (jsb.Graph.lattice(24, 24, 2), jsb.Graph.lattice(27, 27, 3)):
+        res = jsb.run_ensemble(g, p, 24, seed=9, flags=L.MODE_REJECTION_FREE)
+        assert np.all(res.summaries["status"] == 0), np.bincount(res.summaries["status"])
+        assert res.summaries["n_births"].max() > 300
+        res.close()
+    rowptr, colidx = random_geometric_csr(1500, seed=5)
+    g = jsb.Graph.csr(rowptr, colidx)
+    g.set_seed_candidates([7])
+    res = jsb.run_ensemble(g, p, 24, seed=9, flags=L.MODE_REJECTION_FREE)
+    assert np.all(res.summaries["status"] == 0), np.bincount(res.summaries["status"])
+    res.close()
+
+
 def test_fast_mode_invariants_and_log_replay(jsb):
     from jspace_b200 import _lib as L
     g = jsb.Graph.lattice(60, 60, 2)
