@@ -1816,6 +1816,10 @@ int launch_ssa(const RunArgs& args, int grid_blocks, int warps_per_block, void* 
 // exp(−ν (t' − τ)), ν = λ_reference − Σ p_v being the null-iteration rate.
 // =================================================================================================
 constexpr int kFastLevels = 6;        // 32^6 > 2^28 sites
+__constant__ double kInvDeg[33] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10,
+                                   1.0 / 11, 1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19,
+                                   1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28,
+                                   1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32};  // x/deg as x * kInvDeg[deg] (no fp64 division)
 constexpr uint32_t kFastRebuild = 2048;       // events between re-summations of the upper levels
 constexpr uint32_t kFastRefreshLeaves = 8;   // every this many re-summations the leaves are recomputed too
 enum : uint32_t { DS_F_TIME_SELECT = 12, DS_F_KIND_NBR = 13, DS_F_BOUNDARY = 11 };
@@ -1837,6 +1841,7 @@ struct FCtx {
   Key key;
   int64_t local_idx;
   int lane;
+  int lane_delta;            // lattice: vertex offset of this lane's direction slot (lanes 0..5)
   bool track_ids;
 };
 
@@ -1937,8 +1942,8 @@ __device__ __forceinline__ double f_rate(const FCtx& X, const FHood& h, uint32_t
   const uint32_t deg = (uint32_t)__popc(h.present);
   double mpart = 0.0;
   if (deg > 0) {
-    bpart = (X.c_alpha[h.own - 1] * (double)__popc(adm_mask)) / (double)deg;
-    mpart = (X.P->rate_migration * (double)__popc(h.empty)) / (double)deg;
+    bpart = (X.c_alpha[h.own - 1] * (double)__popc(adm_mask)) * kInvDeg[deg];
+    mpart = (X.P->rate_migration * (double)__popc(h.empty)) * kInvDeg[deg];
   }
   return bpart + X.P->rate_death + mpart;
 }
@@ -1978,7 +1983,7 @@ __device__ __forceinline__ FWarpHood f_warp_gather(const FCtx& X, uint32_t x) {
   if (g.kind == 0) {
     const uint32_t mask = lattice_mask(g, x);
     h.present = lane < 6 && ((mask >> lane) & 1u);
-    h.u = f_slot_site(X, x, (uint32_t)lane < 6u ? (uint32_t)lane : 0u);
+    h.u = (uint32_t)((int)x + X.lane_delta);
   } else {
     const uint32_t row0 = g.rowptr[x], deg = g.rowptr[x + 1] - row0;
     h.present = (uint32_t)lane < deg && lane < 31;
@@ -2019,7 +2024,7 @@ __device__ __forceinline__ void f_apply_change(const FCtx& X, uint32_t x, uint32
     const int dadm = (int)f_admissible(X, h.cu, b) - (int)f_admissible(X, h.cu, a);
     const int demp = (int)(b == 0) - (int)(a == 0);
     if (dadm != 0 || demp != 0) {
-      const double delta = (X.c_alpha[h.cu - 1] * (double)dadm + mig * (double)demp) / (double)f_site_degree(X, h.u);
+      const double delta = (X.c_alpha[h.cu - 1] * (double)dadm + mig * (double)demp) * kInvDeg[f_site_degree(X, h.u)];
       X.lvl[0][h.u] = h.leaf + delta;
       f_push_up(X, h.u, delta);
     }
@@ -2030,7 +2035,7 @@ __device__ __forceinline__ void f_apply_change(const FCtx& X, uint32_t x, uint32
     double p = 0.0;
     if (b != 0) {
       p = X.P->rate_death;
-      if (h.deg > 0) p = (X.c_alpha[b - 1] * (double)adm) / (double)h.deg + X.P->rate_death + (mig * (double)emp) / (double)h.deg;
+      if (h.deg > 0) p = (X.c_alpha[b - 1] * (double)adm) * kInvDeg[h.deg] + X.P->rate_death + (mig * (double)emp) * kInvDeg[h.deg];
     }
     X.lvl[0][x] = p;
     const double delta = p - h.own_leaf;
@@ -2420,14 +2425,14 @@ __device__ __noinline__ void f_outputs(const FCtx& X, const FRep& r) {
 }
 
 // apply the state-changing event that fires on site v (resid = offset inside v's rate interval)
-__device__ __forceinline__ bool f_event(const FCtx& X, FRep& r, uint32_t v, double resid, uint64_t w_nbr) {
+__device__ __forceinline__ bool f_event(const FCtx& X, FRep& r, uint32_t v, double resid) {
   const DevPoint& P = *X.P;
   const int lane = X.lane;
   const FWarpHood hv = f_warp_gather(X, v);  // round trip: v, its neighbours, their rates
   const uint32_t c = hv.own;
   const uint32_t emp_mask = __ballot_sync(FULL, hv.present && hv.cu == 0);
   const uint32_t adm_mask = __ballot_sync(FULL, hv.present && f_admissible(X, c, hv.cu));
-  const double bpart = hv.deg ? (X.c_alpha[c - 1] * (double)__popc(adm_mask)) / (double)hv.deg : 0.0;
+  const double bpart = (X.c_alpha[c - 1] * (double)__popc(adm_mask)) * kInvDeg[hv.deg];
   int kind = resid < bpart ? 0 : (resid < bpart + P.rate_death ? 1 : 2);  // birth | death | migration
   if (kind == 0 && adm_mask == 0) kind = 1;  // rounding at a part boundary
   if (kind == 2 && emp_mask == 0) kind = 1;
@@ -2440,7 +2445,12 @@ __device__ __forceinline__ bool f_event(const FCtx& X, FRep& r, uint32_t v, doub
     f_apply_change(X, v, c, 0, hv);
   } else {
     const uint32_t pool = kind == 0 ? adm_mask : emp_mask;
-    const uint32_t want = bounded(X.key, w_nbr, (uint32_t)__popc(pool), r.it, DS_F_KIND_NBR, 0, 1);
+    uint32_t want = 0;
+    if (__popc(pool) > 1) {  // a second Philox block only when there is a choice
+      uint64_t wc, wd;
+      draw_block(X.key, r.it, 0, DS_F_KIND_NBR, 0, wc, wd);
+      want = bounded(X.key, wd, (uint32_t)__popc(pool), r.it, DS_F_KIND_NBR, 0, 1);
+    }
     uint32_t m = pool;
     for (uint32_t q = 0; q < want; ++q) m &= m - 1;  // the want-th admissible / empty neighbour
     const int slot = __ffs(m) - 1;
@@ -2538,10 +2548,10 @@ __device__ __forceinline__ void f_run(const FCtx& X) {
       break;
     }
     r.it += 1;
-    uint64_t wa, wb, wc, wd;
+    uint64_t wa, wb;
     draw_block(X.key, r.it, 0, DS_F_TIME_SELECT, 0, wa, wb);
-    draw_block(X.key, r.it, 0, DS_F_KIND_NBR, 0, wc, wd);
-    const double t_new = r.t + (-contract_log(u01_open(wa))) / Lam;
+    // (2) statistical mode: the library log is enough (no bit-exactness contract here)
+    const double t_new = r.t + (-log(u01_open(wa))) / Lam;
     const double nu = fmax(r.wsum + dm * (double)r.n - Lam, 0.0);  // rate of the reference's null iterations
     FPROF(1);
 
@@ -2596,13 +2606,12 @@ __device__ __forceinline__ void f_run(const FCtx& X) {
     }
     FPROF(2);
     r.t = t_new;
-    if (!f_event(X, r, v, resid, wd)) break;
+    if (!f_event(X, r, v, resid)) break;
     FPROF(3);
     if (excise_after) {
       r.bott_id = next_bott;
       { FCtx xc = X; FRep rc = r; f_excision(xc, rc, tbv, ratio); r = rc; }
     }
-    (void)wc;
   }
 #ifdef JSB_PROFILE
   if (lane == 0 && (X.local_idx < 2 || r.n_births > 60000))
@@ -2648,6 +2657,10 @@ __global__ void __launch_bounds__(384, 1) fast_kernel(const __grid_constant__ Ru
   }
   X.top = k;
   for (int q = k + 1; q < kFastLevels; ++q) { X.lvl[q] = nullptr; X.lvl_n[q] = 0; }
+  {
+    const int plane = (int)(A.g.n1 * A.g.n2), n1 = (int)A.g.n1;
+    X.lane_delta = lane == 0 ? -plane : lane == 1 ? -n1 : lane == 2 ? -1 : lane == 3 ? 1 : lane == 4 ? n1 : lane == 5 ? plane : 0;
+  }
   X.key.k0 = (uint32_t)A.seed ^ 0xFA57FA57u;  // a stream family of its own
   X.key.k1 = (uint32_t)(A.seed >> 32);
   X.track_ids = (A.flags & (JSB_OUT_EVENTS | JSB_OUT_LATTICE)) != 0;
