@@ -120,7 +120,7 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t nv, uint32_t arena_cap, u
   L.g_B = o;      o = jsb_align16(o + 8ull * (kTab + 8));
   L.g_w = o;      o = jsb_align16(o + 8ull * (kTab + 8));
   L.g_c = o;      o = jsb_align16(o + 8ull * (kTab + 8));
-  L.ftree = o;    o = jsb_align16(o + 8ull * ((uint64_t)nv / 31 + 128));  // fast mode: upper tree levels (geometric sum)
+  L.ftree = o;    o = jsb_align16(o + 8ull * ((uint64_t)nv / 31 + 256));  // fast mode: upper tree levels (geometric sum)
   L.total = (o + 255) & ~uint64_t(255);
   return L;
 }

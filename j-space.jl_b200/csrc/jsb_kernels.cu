@@ -1815,7 +1815,7 @@ int launch_ssa(const RunArgs& args, int grid_blocks, int warps_per_block, void* 
 // boundary τ in (t, t'), the event belongs to the loop iteration that crosses τ with probability
 // exp(−ν (t' − τ)), ν = λ_reference − Σ p_v being the null-iteration rate.
 // =================================================================================================
-constexpr int kFastLevels = 6;        // 32^6 > 2^28 sites
+constexpr int kFastLevels = 7;        // 32^6 > 2^28 sites, plus the single-entry root
 __constant__ double kInvDeg[33] = {0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10,
                                    1.0 / 11, 1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19,
                                    1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28,
@@ -1834,7 +1834,7 @@ struct FCtx {
   uint32_t *inds, *samp;
   double* lvl[kFastLevels];  // lvl[0] = per-site rates, lvl[k][i] = sum of lvl[k-1][32i .. 32i+31]
   uint32_t lvl_n[kFastLevels];
-  int top;                   // lvl[top] has at most 32 entries
+  int top;                   // lvl[top] is the root: one entry = the total rate (top = 0 only when nv == 1)
   uint32_t* c_cnt;
   double* c_alpha;
   uint16_t *c_parent, *c_label;
@@ -2020,9 +2020,10 @@ __device__ __forceinline__ void f_push_up(const FCtx& X, uint32_t s, double delt
 __device__ __forceinline__ void f_apply_change(const FCtx& X, uint32_t x, uint32_t a, uint32_t b, const FWarpHood& h) {
   const int lane = X.lane;
   const double mig = X.P->rate_migration;
+  const bool contact = X.P->rule == JSB_RULE_CONTACT;
   if (h.present && h.cu != 0) {
-    const int dadm = (int)f_admissible(X, h.cu, b) - (int)f_admissible(X, h.cu, a);
     const int demp = (int)(b == 0) - (int)(a == 0);
+    const int dadm = contact ? demp : (int)f_admissible(X, h.cu, b) - (int)f_admissible(X, h.cu, a);
     if (dadm != 0 || demp != 0) {
       const double delta = (X.c_alpha[h.cu - 1] * (double)dadm + mig * (double)demp) * kInvDeg[f_site_degree(X, h.u)];
       X.lvl[0][h.u] = h.leaf + delta;
@@ -2030,7 +2031,7 @@ __device__ __forceinline__ void f_apply_change(const FCtx& X, uint32_t x, uint32
     }
   }
   const uint32_t emp = (uint32_t)__popc(__ballot_sync(FULL, h.present && h.cu == 0));
-  const uint32_t adm = (uint32_t)__popc(__ballot_sync(FULL, h.present && b != 0 && f_admissible(X, b, h.cu)));
+  const uint32_t adm = contact ? emp : (uint32_t)__popc(__ballot_sync(FULL, h.present && b != 0 && f_admissible(X, b, h.cu)));
   if (lane == 31) {
     double p = 0.0;
     if (b != 0) {
@@ -2114,8 +2115,8 @@ __device__ __forceinline__ bool f_select(const FCtx& X, double target64, uint32_
   uint32_t idx = 0;
   float target = (float)target64;
 #pragma unroll
-  for (int k = kFastLevels - 1; k >= 0; --k) {
-    if (k > X.top) continue;
+  for (int k = kFastLevels - 2; k >= 0; --k) {
+    if (k >= X.top && X.top > 0) continue;  // start below the root
     const uint32_t base = idx * 32u;
     const uint32_t c = base + (uint32_t)X.lane;
     const double val64 = c < X.lvl_n[k] ? X.lvl[k][c] : 0.0;
@@ -2431,7 +2432,7 @@ __device__ __forceinline__ bool f_event(const FCtx& X, FRep& r, uint32_t v, doub
   const FWarpHood hv = f_warp_gather(X, v);  // round trip: v, its neighbours, their rates
   const uint32_t c = hv.own;
   const uint32_t emp_mask = __ballot_sync(FULL, hv.present && hv.cu == 0);
-  const uint32_t adm_mask = __ballot_sync(FULL, hv.present && f_admissible(X, c, hv.cu));
+  const uint32_t adm_mask = P.rule == JSB_RULE_CONTACT ? emp_mask : __ballot_sync(FULL, hv.present && f_admissible(X, c, hv.cu));
   const double bpart = (X.c_alpha[c - 1] * (double)__popc(adm_mask)) * kInvDeg[hv.deg];
   int kind = resid < bpart ? 0 : (resid < bpart + P.rate_death ? 1 : 2);  // birth | death | migration
   if (kind == 0 && adm_mask == 0) kind = 1;  // rounding at a part boundary
@@ -2542,7 +2543,7 @@ __device__ __forceinline__ void f_run(const FCtx& X) {
       r.since_rebuild = 0;
     }
     FPROF(0);
-    const double Lam = f_warp_sum((uint32_t)lane < X.lvl_n[X.top] ? X.lvl[X.top][lane] : 0.0);
+    const double Lam = X.lvl[X.top][0];  // the root of the sum tree
     if (!(Lam > 0.0)) {  // nothing can change any more: the reference idles through null events to Tf
       r.t = P.Tf;
       break;
@@ -2649,7 +2650,7 @@ __global__ void __launch_bounds__(384, 1) fast_kernel(const __grid_constant__ Ru
   double* up = A.fast_smem_tree ? reinterpret_cast<double*>(sw + kFastFixed)
                                 : reinterpret_cast<double*>(base + L.ftree);
   int k = 0;
-  while (X.lvl_n[k] > 32 && k + 1 < kFastLevels) {
+  while (X.lvl_n[k] > 1 && k + 1 < kFastLevels) {
     X.lvl_n[k + 1] = (X.lvl_n[k] + 31) / 32;
     X.lvl[k + 1] = up;
     up += X.lvl_n[k + 1];
@@ -2695,7 +2696,7 @@ __global__ void __launch_bounds__(384, 1) fast_kernel(const __grid_constant__ Ru
 static size_t fast_upper_entries(uint32_t nv) {
   size_t total = 0;
   uint32_t n = nv;
-  while (n > 32) { n = (n + 31) / 32; total += n; }
+  while (n > 1) { n = (n + 31) / 32; total += n; }
   return total;
 }
 
