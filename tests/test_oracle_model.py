@@ -125,3 +125,29 @@ def test_lattice_graph_restatement(oracle):
     assert g3.nv == 50 ** 3 and g3.neighbors(61426).tolist() == [58926, 61376, 61425, 61427, 61476, 63926]
     ga = oracle.Graph.dense_file(os.path.join(HERE, "golden", "Example_adj_matrix.txt"))
     assert ga.nv == 10 and ga.closeness_argmax().tolist() == [1, 2]
+
+
+@pytest.mark.parametrize("model,extra", [("contact", dict(t_bottleneck=[25.0], ratio_bottleneck=[0.8])),
+                                         ("contact", dict(t_bottleneck=[30.0], ratio_bottleneck=[0.03])),
+                                         ("voter", {}), ("hvoter", {})])
+def test_oracle_equals_independent_python_restatement(oracle, model, extra):
+    """tests/pymodel.py restates the reference loop a second time, in plain Python, from the
+    reference source and the draw contract; the C++ oracle must reproduce it bit for bit."""
+    import pymodel
+    base = dict(Tf=45.0, rate_birth=0.25, rate_death=0.03, rate_migration=0.03, mu_driver=0.06, adv_mean=0.4, adv_std=0.1)
+    for (row, col), stream in (((9, 7), 0), ((12, 12), 3), ((6, 10), 5)):
+        df, alpha, set_mut, it, t = pymodel.simulate(row, col, base["Tf"], base["rate_birth"], base["rate_death"],
+                                                     base["rate_migration"], base["mu_driver"], base["adv_mean"],
+                                                     base["adv_std"], model, 4321, stream,
+                                                     extra.get("t_bottleneck", ()), extra.get("ratio_bottleneck", ()))
+        r = oracle.Run(oracle.Graph.lattice(2, row, col), oracle.make_params(**dict(base, rule=model, **extra)), 4321,
+                       stream, faithful=True)
+        ev = r.events
+        assert len(ev) == len(df) and r.summary["n_iterations"] == it and r.summary["t_final"] == t
+        for k, row_py in enumerate(df):
+            e = ev[k]
+            got = (int(e["type"]), float(e["time"]), int(e["cell"]), int(e["parent"]), int(e["site"]), int(e["site2"]),
+                   int(e["clone"]), int(e["label"]), int(e["flags"]))
+            assert got == row_py, (model, (row, col), k, got, row_py)
+        assert r.clones["alpha"].tolist() == alpha
+        assert [(int(c["parent"]), int(c["label"])) for c in r.clones] == set_mut
