@@ -52,8 +52,8 @@ struct DevPoint {
 
 // Workspace layout per slot (all offsets 16-byte aligned); computed identically on host and device.
 struct WsLayout {
-  uint64_t clone, cellid, A, a_head, arena, inds, samp, c_off, c_len, c_cap, c_alpha, c_parent, c_label, g_B, g_w, g_c,
-      ftree, total;
+  uint64_t clone, cellid, A, a_head, arena, inds, samp, c_cnt, c_cap, c_alpha, c_parent, c_label, g_w, g_c, ftree,
+      total;
 };
 struct RunArgs {
   DevGraph g;
@@ -92,9 +92,9 @@ struct RunArgs {
   uint32_t* out_cell;
   uint32_t* out_lists;  // [n_local][2][nv]: cs_alive then concatenated ca_subpop
   unsigned long long* work_counter;
-  // longest-first scheduling: a pilot pass runs every replicate for `pilot_iters`
-  // iterations and writes a work estimate; the full pass then takes replicates in `order`
   uint32_t fast_smem_tree;  // rejection-free mode: upper tree levels live in shared memory
+  // optional longest-first scheduling: a pilot pass runs every replicate for
+  // `pilot_iters` iterations and writes a work estimate; the full pass then takes replicates in `order`
   const uint32_t* order;  // nullptr: natural order
   uint64_t pilot_iters;   // > 0: pilot pass (no outputs except prio)
   float* prio;
@@ -111,13 +111,11 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t nv, uint32_t arena_cap, u
   L.arena = o;    o = jsb_align16(o + (uint64_t)site_bytes * arena_cap + 32);
   L.inds = o;     o = jsb_align16(o + 4ull * nv);
   L.samp = o;     o = jsb_align16(o + 4ull * nv);
-  L.c_off = o;    o = jsb_align16(o + 4ull * kTab);
-  L.c_len = o;    o = jsb_align16(o + 4ull * kTab);
+  L.c_cnt = o;    o = jsb_align16(o + 4ull * kTab);  // rejection-free mode: clone sizes (exact mode keeps them in smem)
   L.c_cap = o;    o = jsb_align16(o + 4ull * kTab);
   L.c_alpha = o;  o = jsb_align16(o + 8ull * kTab);
   L.c_parent = o; o = jsb_align16(o + 2ull * kTab);
   L.c_label = o;  o = jsb_align16(o + 2ull * kTab);
-  L.g_B = o;      o = jsb_align16(o + 8ull * (kTab + 8));
   L.g_w = o;      o = jsb_align16(o + 8ull * (kTab + 8));
   L.g_c = o;      o = jsb_align16(o + 8ull * (kTab + 8));
   L.ftree = o;    o = jsb_align16(o + 8ull * ((uint64_t)nv / 31 + 256));  // fast mode: upper tree levels (geometric sum)

@@ -2638,7 +2638,7 @@ __global__ void __launch_bounds__(384, 1) fast_kernel(const __grid_constant__ Ru
   X.cellid = reinterpret_cast<uint32_t*>(base + L.cellid);
   X.inds = reinterpret_cast<uint32_t*>(base + L.inds);
   X.samp = reinterpret_cast<uint32_t*>(base + L.samp);
-  X.c_cnt = reinterpret_cast<uint32_t*>(base + L.c_len);
+  X.c_cnt = reinterpret_cast<uint32_t*>(base + L.c_cnt);
   X.c_parent = reinterpret_cast<uint16_t*>(base + L.c_parent);
   X.c_label = reinterpret_cast<uint16_t*>(base + L.c_label);
   DevPoint* sP = reinterpret_cast<DevPoint*>(sw);
