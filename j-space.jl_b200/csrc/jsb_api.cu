@@ -618,12 +618,24 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     const bool fast_mode = (opts->flags & JSB_MODE_REJECTION_FREE) != 0;
     int wpb = 1;
     if ((fast_mode ? fast_prepare(a, opts->warps_per_sm, &wpb) : ssa_prepare(a, opts->warps_per_sm, &wpb)) != 0) { rc = fail(JSB_ECUDA, "cannot configure shared memory for the SSA kernel"); goto done; }
-    // one block per SM; spread small ensembles over all SMs before stacking warps
+    // one block per SM; spread small ensembles over all SMs before stacking warps.  In the exact
+    // mode warps without a replicate help the busy warps of their block (lookahead windows), so a
+    // small ensemble still gets up to twice as many warps as replicates.
+    const bool helpers = !fast_mode && !std::getenv("JSB_NO_HELPERS");
+    int grid;
     {
-      int64_t per_sm = (n_local + prop.multiProcessorCount - 1) / prop.multiProcessorCount;
-      if (per_sm < wpb) wpb = (int)std::max<int64_t>(1, per_sm);
+      const int64_t sms = prop.multiProcessorCount;
+      const int64_t per_sm = (n_local + sms - 1) / sms;
+      if (fast_mode || !helpers) {
+        if (per_sm < wpb) wpb = (int)std::max<int64_t>(1, per_sm);
+        grid = (int)std::min<int64_t>((n_local + wpb - 1) / wpb, sms);
+      } else {
+        if (2 * per_sm < wpb) wpb = (int)std::max<int64_t>(2, 2 * per_sm);
+        grid = (int)std::min<int64_t>(n_local, sms);
+        a.static_map = (uint64_t)n_local < (uint64_t)grid * wpb ? 1u : 0u;
+        a.helpers = 1;
+      }
     }
-    int grid = (int)std::min<int64_t>((n_local + wpb - 1) / wpb, (int64_t)prop.multiProcessorCount);
     const uint64_t slots = (uint64_t)grid * wpb;
 
     uint32_t arena_cap = (uint32_t)std::min<uint64_t>(4ull * g->nv + 2ull * kMinListCap * kTab, 0xFFFFFF00ull);

@@ -93,6 +93,8 @@ struct RunArgs {
   uint32_t* out_lists;  // [n_local][2][nv]: cs_alive then concatenated ca_subpop
   unsigned long long* work_counter;
   uint32_t fast_smem_tree;  // rejection-free mode: upper tree levels live in shared memory
+  uint32_t helpers;         // exact mode: idle warps of a block evaluate the next window for busy ones
+  uint32_t static_map;      // fewer replicates than warps: replicate idx is owned by block idx % grid
   // optional longest-first scheduling: a pilot pass runs every replicate for
   // `pilot_iters` iterations and writes a work estimate; the full pass then takes replicates in `order`
   const uint32_t* order;  // nullptr: natural order

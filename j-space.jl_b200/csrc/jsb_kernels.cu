@@ -1509,10 +1509,79 @@ __device__ __noinline__ SlowOut slow_scan(const Ctx<T>& X, const Rep& r, double 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-cooperative lookahead.  A warp that has no replicate left (the tail of an ensemble, or an
+// ensemble smaller than the machine) attaches to a busy warp of its block and evaluates the NEXT
+// window of 32 iterations for it, against the same state, while the owner evaluates the current
+// one.  If the owner's window turns out to be all null events it commits the helper's window too
+// (64 iterations per evaluation latency instead of 32).  The owner never changes any state while a
+// request is outstanding, and the helper only ever reads; both sit in the same block, so the
+// mailbox lives in shared memory.  Results are identical by construction (same evaluation code,
+// same state) — the parity tests run with helpers active.
+// ---------------------------------------------------------------------------------------------
+struct HelpMail {
+  uint32_t req, ack;      // owner bumps req for every posted window; helper sets ack = req when done
+  uint32_t helper, done;  // a helper is attached; the owner has no work left
+  uint32_t S, n, search_top, stream;
+  unsigned long long it_base;  // the helper evaluates iterations it_base+1 .. it_base+32
+  double lambda, guard, theta;
+  uint32_t usable, effm, cls, x, cell, pos;  // first state-changing lane of the helper's window
+  uint32_t pad[2];
+  double dt[32];
+};
+static_assert(sizeof(HelpMail) % 16 == 0, "mailbox keeps the 16-byte alignment of the smem slices");
+
+template <typename T>
+__device__ __noinline__ void helper_serve(Ctx<T> X, volatile HelpMail* M) {
+  const int lane = X.lane;
+  uint32_t last = M->ack;
+  for (;;) {
+    uint32_t rq;
+    for (;;) {
+      rq = M->req;
+      if (rq != last) break;
+      if (M->done) return;
+      __nanosleep(40);
+    }
+    __threadfence_block();
+    Rep r;
+    r.it = M->it_base; r.S = M->S; r.n = M->n;
+    r.lambda = M->lambda; r.guard = M->guard; r.theta = M->theta;
+    X.search_top = M->search_top;
+    X.key.stream = M->stream;
+    const uint64_t q = r.it + 1 + (uint64_t)lane;
+    uint64_t wa, wb, wc, wd;
+    draw_block(X.key, q, 0, DS_TIME_CLASS, 0, wa, wb);
+    draw_block(X.key, q, 0, DS_CELL_NBR, 0, wc, wd);
+    const double dt = (-contract_log(u01_open(wa))) * r.theta;
+    const uint32_t nb = r.S + 2;
+    const double key = u01_53(wb) * r.lambda;
+    const uint32_t c = class_search(X.sB, X.search_top, key);
+    const uint32_t cc = c < nb ? c : nb - 1;
+    const double hi_b = lds_f64(X.sB + cc * 8u), lo_b = lds_f64(X.sB + (cc > 0 ? cc - 1 : 0) * 8u);
+    const bool unc = c >= nb || (hi_b - key <= r.guard) || (cc > 0 && key - lo_b <= r.guard);
+    const uint32_t anyunc = __ballot_sync(FULL, unc);
+    uint32_t x = 0, cell = 0, pos = 0;
+    bool valid = false, eff = false;
+    if (!anyunc) {  // inside the guard band the owner decides with its exact table
+      eval_member(X, r, q, c, wc, x, cell, valid);
+      eff = eval_target(X, r, q, c, cell, valid, wd, pos);
+    }
+    const uint32_t effm = __ballot_sync(FULL, eff);
+    M->dt[lane] = dt;
+    if (effm && lane == __ffs(effm) - 1) { M->cls = c; M->x = x; M->cell = cell; M->pos = pos; }
+    if (lane == 0) { M->effm = effm; M->usable = anyunc ? 0u : 1u; }
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) M->ack = rq;
+    last = rq;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // One replicate
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ void run_replicate(Ctx<T>& X) {
+__device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M) {
   const RunArgs& A = *X.A;
   const DevPoint& P = *X.P;
   const int lane = X.lane;
@@ -1534,6 +1603,8 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X) {
   const uint32_t wmask = width == 32 ? FULL : ((1u << width) - 1u);
   const uint32_t nv = A.g.nv;
   uint32_t Ucur = 1;  // sub-batches per speculative window (1, 2 or 4), adapted to the run length
+  bool prev_null = false;  // the previous window changed nothing: worth asking a helper for the next-but-one
+  if (force_exact || width != 32u) M = nullptr;
 
   PROF_DECL
   for (;;) {
@@ -1546,6 +1617,20 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X) {
     if (r.dirty_from != kNone) prof_fold += (long long)r.S - (long long)(r.dirty_from < r.S ? r.dirty_from : r.S);
 #endif
     if (r.dirty_from != kNone) { refold(X, r); PROF_ADD(PH_REFOLD); }
+
+    // ---- ask an attached helper warp for the window after this one ----------------------------------
+    bool posted = false;
+    if (M && prev_null && M->helper != 0 && M->ack == M->req) {
+      if (lane == 0) {
+        M->S = r.S; M->n = r.n; M->search_top = X.search_top; M->stream = X.key.stream;
+        M->it_base = r.it + 32;
+        M->lambda = r.lambda; M->guard = r.guard; M->theta = r.theta;
+        __threadfence_block();
+        M->req = M->req + 1;
+      }
+      __syncwarp();
+      posted = true;
+    }
 
     // ---- speculative window: Ucur sub-batches of 32 iterations ----------------------------------
     double dtv[kMaxSub];
@@ -1603,6 +1688,28 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X) {
     bool do_event = found;
     bool do_snap = false, do_bott = false;
     double tb_fire = 0.0, ratio_fire = 0.0;
+    bool from_helper = false;
+
+    if (posted) {
+      // the helper must be finished before anything changes (it reads the lists) and before its
+      // window is used; it has been running in parallel with this warp's own evaluation
+      while (M->ack != M->req) __nanosleep(20);
+      __threadfence_block();
+      if (!found && !slow && M->usable) {
+        const uint32_t effm2 = M->effm;
+        const uint32_t jE2 = effm2 ? (uint32_t)__ffs(effm2) - 1u : 31u;
+        const double tend2 = time_chain(X.sDt, lane, tend, M->dt[lane], jE2);
+        if (!touches(tend2, 32u + jE2 + 1u)) {  // nothing but that one event inside the second window either
+          r.it += 32u;
+          tend = tend2;
+          j = jE = jE2;
+          ustar = 0;
+          found = do_event = effm2 != 0;
+          from_helper = true;
+        }
+      }
+    }
+    prev_null = !found && !slow;
 
     if (!slow) {
       r.it += (uint64_t)ustar * 32u + jE + 1u;
@@ -1642,9 +1749,10 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X) {
     if (do_event) {
       Eval ej;
       ej.cls = ej.x = ej.cell = ej.pos = 0;
+      if (from_helper) { ej.cls = M->cls; ej.x = M->x; ej.cell = M->cell; ej.pos = M->pos; }
 #pragma unroll
       for (int u = 0; u < kMaxSub; ++u)
-        if ((uint32_t)u == ustar) {
+        if (!from_helper && (uint32_t)u == ustar) {
           ej.cls = __shfl_sync(FULL, cls[u], (int)j);
           ej.x = __shfl_sync(FULL, xx[u], (int)j);
           ej.cell = __shfl_sync(FULL, cell[u], (int)j);
@@ -1686,12 +1794,14 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X) {
 __host__ __device__ inline size_t smem_base_bytes() {
   return sizeof(double) * (kSmemTable + 32) + 2 * sizeof(uint32_t) * kTab + ((sizeof(DevPoint) + 15) & ~size_t(15));
 }
+// the helper mailbox sits at the end of every warp's slice
+__device__ __forceinline__ volatile HelpMail* mail_of(unsigned char* s_dyn, uint32_t smem_per_warp, int warp) {
+  return reinterpret_cast<volatile HelpMail*>(s_dyn + (size_t)(warp + 1) * smem_per_warp - sizeof(HelpMail));
+}
 
+// context of warp slot `warp` of this block (a warp's own slot, or the slot of the warp it helps)
 template <typename T>
-__global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __grid_constant__ RunArgs A) {
-  extern __shared__ __align__(16) unsigned char s_dyn[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+__device__ __forceinline__ Ctx<T> make_ctx(const RunArgs& A, unsigned char* s_dyn, int warp, int lane, DevPoint** sP_out) {
   const uint64_t slot = (uint64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   const WsLayout& L = A.L;
   uint8_t* base = A.ws + slot * A.ws_stride;
@@ -1725,12 +1835,38 @@ __global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __
   X.search_top = 2;
   X.key.k0 = (uint32_t)A.seed;
   X.key.k1 = (uint32_t)(A.seed >> 32);
+  X.key.stream = 0;
   X.track_ids = (A.flags & (JSB_OUT_EVENTS | JSB_OUT_LATTICE)) != 0;
+  X.P = sP;
+  X.local_idx = 0;
+  X.tb = X.ratio = X.tsnap = X.node_rate = nullptr;
+  X.edge_parent = X.edge_child = nullptr;
+  *sP_out = sP;
+  return X;
+}
 
-  for (;;) {
+template <typename T>
+__global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __grid_constant__ RunArgs A) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  DevPoint* sP;
+  Ctx<T> X = make_ctx<T>(A, s_dyn, warp, lane, &sP);
+  volatile HelpMail* myM = mail_of(s_dyn, A.smem_per_warp, warp);
+  if (lane == 0) { myM->req = 0; myM->ack = 0; myM->helper = 0; myM->done = 0; }
+  __syncthreads();  // the only block-wide barrier: mailboxes are initialised before anyone looks
+
+  for (uint32_t round = 0;; ++round) {
     unsigned long long idx = 0;
-    if (lane == 0) idx = atomicAdd(A.work_counter, 1ull);
-    idx = __shfl_sync(FULL, idx, 0);
+    if (A.static_map) {
+      // fewer replicates than warps: block b owns replicates b, b + grid, ...; warp w takes the w-th
+      idx = (unsigned long long)blockIdx.x + (unsigned long long)warp * gridDim.x;
+      if (round > 0) idx = (unsigned long long)A.n_local;
+    } else {
+      if (lane == 0) idx = atomicAdd(A.work_counter, 1ull);
+      idx = __shfl_sync(FULL, idx, 0);
+    }
     if ((long long)idx >= A.n_local) break;
     if (A.order) idx = A.order[idx];
     const int64_t gidx = A.g_begin + (int64_t)idx;
@@ -1752,7 +1888,29 @@ __global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __
     X.node_rate = A.dpool + P->rate_off;
     X.edge_parent = A.ipool + P->edge_off;
     X.edge_child = X.edge_parent + P->n_edges;
-    run_replicate<T>(X);
+    run_replicate<T>(X, A.helpers ? myM : nullptr);
+  }
+
+  if (!A.helpers) return;
+  // no replicate left for this warp: help the busy warps of the block, one at a time
+  if (lane == 0) myM->done = 1;
+  __threadfence_block();
+  __syncwarp();
+  for (;;) {
+    int target = -1;
+    for (int w = 0; w < nwarps && target < 0; ++w) {
+      if (w == warp) continue;
+      volatile HelpMail* m = mail_of(s_dyn, A.smem_per_warp, w);
+      if (m->done || m->helper) continue;
+      uint32_t got = 0;
+      if (lane == 0) got = atomicCAS(const_cast<uint32_t*>(&m->helper), 0u, 1u) == 0u ? 1u : 0u;
+      got = __shfl_sync(FULL, got, 0);
+      if (got) target = w;
+    }
+    if (target < 0) break;
+    DevPoint* oP;
+    Ctx<T> XO = make_ctx<T>(A, s_dyn, target, lane, &oP);
+    helper_serve<T>(XO, mail_of(s_dyn, A.smem_per_warp, target));
   }
 }
 
@@ -1764,8 +1922,8 @@ int ssa_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block) {
   cudaGetDevice(&dev);
   int max_optin = 0;
   if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
-  const size_t with_occ = (smem_base_bytes() + 4ull * words + 15) & ~size_t(15);
-  const size_t without = (smem_base_bytes() + 15) & ~size_t(15);
+  const size_t with_occ = ((smem_base_bytes() + 4ull * words + 15) & ~size_t(15)) + sizeof(HelpMail);
+  const size_t without = ((smem_base_bytes() + 15) & ~size_t(15)) + sizeof(HelpMail);
   int cap = kMaxWarpsPerBlock;
   if (max_warps_per_sm > 0 && max_warps_per_sm < cap) cap = max_warps_per_sm;
   int w_occ = (int)((size_t)max_optin / with_occ);
