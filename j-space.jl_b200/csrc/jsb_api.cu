@@ -556,6 +556,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
   uint32_t *d_out_cell = nullptr, *d_out_lists = nullptr;
   uint32_t* d_order = nullptr;
   float* d_prio = nullptr;
+  unsigned long long* d_trace = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t stream = nullptr;
   int prev_dev = 0;
@@ -620,7 +621,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     if ((fast_mode ? fast_prepare(a, opts->warps_per_sm, &wpb) : ssa_prepare(a, opts->warps_per_sm, &wpb)) != 0) { rc = fail(JSB_ECUDA, "cannot configure shared memory for the SSA kernel"); goto done; }
     // one block per SM; spread small ensembles over all SMs before stacking warps.  In the exact
     // mode warps without a replicate help the busy warps of their block (lookahead windows), so a
-    // small ensemble still gets up to twice as many warps as replicates.
+    // small ensemble still gets up to 1 + kMaxHelp warps per replicate.
     const bool helpers = !fast_mode && !std::getenv("JSB_NO_HELPERS");
     int grid;
     {
@@ -630,7 +631,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
         if (per_sm < wpb) wpb = (int)std::max<int64_t>(1, per_sm);
         grid = (int)std::min<int64_t>((n_local + wpb - 1) / wpb, sms);
       } else {
-        if (2 * per_sm < wpb) wpb = (int)std::max<int64_t>(2, 2 * per_sm);
+        if ((1 + kMaxHelp) * per_sm < wpb) wpb = (int)((1 + kMaxHelp) * per_sm);
         grid = (int)std::min<int64_t>(n_local, sms);
         a.static_map = (uint64_t)n_local < (uint64_t)grid * wpb ? 1u : 0u;
         a.helpers = 1;
@@ -701,6 +702,11 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     a.out_clone = d_out_clone; a.out_cell = d_out_cell; a.out_lists = d_out_lists;
     a.work_counter = d_counters;
 
+    const char* trace_path = std::getenv("JSB_TRACE");  // debug: per-replicate start/end/SM/iterations, raw u64[4]
+    if (trace_path) {
+      CUDA_TRY(cudaMalloc(&d_trace, sizeof(unsigned long long) * 4 * n_local));
+      a.trace = d_trace;
+    }
     pt.mark("setup + allocations");
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
@@ -715,6 +721,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
       RunArgs pa = a;
       pa.pilot_iters = 8192;
       pa.prio = d_prio;
+      pa.trace = nullptr;
       pa.flags = 0;
       pa.clone_pool = nullptr;
       pa.out_clone = nullptr; pa.out_cell = nullptr; pa.out_lists = nullptr; pa.snaps = nullptr;
@@ -745,6 +752,11 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
       res->kernel_ms = ms;
     }
 
+    if (trace_path) {
+      std::vector<unsigned long long> tr((size_t)n_local * 4);
+      CUDA_TRY(cudaMemcpy(tr.data(), d_trace, sizeof(unsigned long long) * tr.size(), cudaMemcpyDeviceToHost));
+      if (FILE* f = std::fopen(trace_path, "wb")) { std::fwrite(tr.data(), sizeof(unsigned long long), tr.size(), f); std::fclose(f); }
+    }
     pt.mark("simulation kernel");
     // ---- copy back ------------------------------------------------------------------------
     res->summaries.resize((size_t)n_local);
@@ -827,7 +839,7 @@ done:
   cudaFree(d_points); cudaFree(d_dpool); cudaFree(d_ipool); cudaFree(d_ws); cudaFree(d_sum); cudaFree(d_clones);
   cudaFree(d_counters); cudaFree(d_clone_off); cudaFree(d_log); cudaFree(d_gather); cudaFree(d_chunk_next);
   cudaFree(d_chunk_owner); cudaFree(d_chunk_seq); cudaFree(d_ev_off); cudaFree(d_snaps); cudaFree(d_out_clone);
-  cudaFree(d_out_cell); cudaFree(d_out_lists); cudaFree(d_order); cudaFree(d_prio);
+  cudaFree(d_out_cell); cudaFree(d_out_lists); cudaFree(d_order); cudaFree(d_prio); cudaFree(d_trace);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (stream) cudaStreamDestroy(stream);

@@ -15,6 +15,7 @@ constexpr int kMinListCap = 32;    // initial capacity of a ca_subpop list in th
 #ifndef JSB_MAXWARPS
 #define JSB_MAXWARPS 12
 #endif
+constexpr int kMaxHelp = 4;  // lookahead depth: helper warps per busy warp (exact mode)
 constexpr int kMaxWarpsPerBlock = JSB_MAXWARPS;  // one block per SM; warps per block chosen at launch
 
 // Draw sites of the draw contract; ctr.w = site << 28 | seq
@@ -99,6 +100,7 @@ struct RunArgs {
   // `pilot_iters` iterations and writes a work estimate; the full pass then takes replicates in `order`
   const uint32_t* order;  // nullptr: natural order
   uint64_t pilot_iters;   // > 0: pilot pass (no outputs except prio)
+  unsigned long long* trace;  // JSB_TRACE: per replicate {start ns, end ns, sm<<8|warp, iterations}
   float* prio;
 };
 

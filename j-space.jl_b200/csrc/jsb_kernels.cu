@@ -49,10 +49,15 @@ enum { PH_REFOLD, PH_DRAWS, PH_CLASS, PH_EVAL, PH_TIME, PH_BIRTH, PH_DEATH, PH_M
 #define PROF_DECL long long prof_c[PH_N] = {0}; long long prof_n[PH_N] = {0}; long long prof_t0 = 0; long long prof_fold = 0;
 #define PROF_T0() prof_t0 = clock64()
 #define PROF_ADD(ph) do { long long _t = clock64(); prof_c[ph] += _t - prof_t0; prof_n[ph]++; prof_t0 = _t; } while (0)
+__device__ long long g_sub[8];  // sub-phase cycle totals of one profiled replicate (lane 0)
+#define SUB_T0() long long _s0 = clock64()
+#define SUB_ADD(k) do { long long _s1 = clock64(); if ((threadIdx.x & 31) == 0) g_sub[k] += _s1 - _s0; _s0 = _s1; } while (0)
 #else
 #define PROF_DECL
 #define PROF_T0()
 #define PROF_ADD(ph)
+#define SUB_T0()
+#define SUB_ADD(k)
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -163,6 +168,68 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
   return v;
 }
+// global load that asks L1 to keep the line (the per-replicate fitness table is re-read after every event)
+__device__ __forceinline__ double ldg_keep_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ void lds_v2f64(uint32_t a, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts_v2f64(uint32_t a, double x, double y) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+// Sequential left fold acc <- fl(acc + v[k]), k = 0..count-1, over doubles in shared memory at the
+// 16-byte aligned address `sa`; with STORE the running value replaces v[k] (written by `writer`
+// lanes only; every lane runs the same chain).  A dependent fp64 add issues every ~8 cycles on
+// sm_100 and a shared-memory load takes ~30, so the loop is double-buffered in groups of eight:
+// the next group is requested before the current one is added (measured 10.7 cycles per element
+// against 14-28 for simpler loop shapes, scripts/micro/fold2.cu).  The prefetch address is clamped
+// to the last group instead of being predicated, which keeps the body free of branches.
+#define JSB_LOAD8(v, o)                                                                            \
+  {                                                                                                \
+    lds_v2f64((o), v[0], v[1]); lds_v2f64((o) + 16u, v[2], v[3]);                                  \
+    lds_v2f64((o) + 32u, v[4], v[5]); lds_v2f64((o) + 48u, v[6], v[7]);                            \
+  }
+#define JSB_CHAIN8(v, o)                                                                           \
+  {                                                                                                \
+    const double p0 = acc + v[0]; const double p1 = p0 + v[1]; if (STORE && writer) sts_v2f64((o), p0, p1);        \
+    const double p2 = p1 + v[2]; const double p3 = p2 + v[3]; if (STORE && writer) sts_v2f64((o) + 16u, p2, p3);   \
+    const double p4 = p3 + v[4]; const double p5 = p4 + v[5]; if (STORE && writer) sts_v2f64((o) + 32u, p4, p5);   \
+    const double p6 = p5 + v[6]; acc = p6 + v[7]; if (STORE && writer) sts_v2f64((o) + 48u, p6, acc);              \
+  }
+template <bool STORE>
+__device__ __forceinline__ double fold_chain(uint32_t sa, uint32_t count, double acc, bool writer) {
+  const uint32_t ngrp = count >> 3;
+  if (ngrp) {
+    const uint32_t last_g = sa + (ngrp - 1u) * 64u;
+    uint32_t o = sa;
+    double a[8], b[8];
+    JSB_LOAD8(a, o);
+    for (uint32_t g = 0;;) {
+      { const uint32_t on = min(o + 64u, last_g); JSB_LOAD8(b, on); }
+      JSB_CHAIN8(a, o);
+      if (++g == ngrp) break;
+      o += 64u;
+      { const uint32_t on = min(o + 64u, last_g); JSB_LOAD8(a, on); }
+      JSB_CHAIN8(b, o);
+      if (++g == ngrp) break;
+      o += 64u;
+    }
+  }
+  for (uint32_t k = ngrp << 3; k < count; ++k) {
+    acc = acc + lds_f64(sa + k * 8u);
+    if (STORE && writer) sts_f64(sa + k * 8u, acc);
+  }
+  return acc;
+}
+#undef JSB_LOAD8
+#undef JSB_CHAIN8
+
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -694,36 +761,41 @@ __device__ __forceinline__ void refold(Ctx<T>& X, Rep& r) {
   double* __restrict__ B = X.B;
   const double* __restrict__ alpha = X.c_alpha;
   const uint32_t* __restrict__ clen = X.c_len;
-  // phase A: B[i] <- w_i = α_i·n_i for every i >= from (parallel; all loads in flight at once)
-  for (uint32_t i = from + lane; i < S; i += 32) B[i] = alpha[i] * (double)clen[i];  // :693
-  __syncwarp();
-  // phase B: in-place sequential left fold (the reference's `sum`), every lane redundantly
-  double acc = from ? B[from - 1] : 0.0;  // 0.0 + w_0 == w_0 exactly
-  uint32_t i = from;
-  for (; i < S && (i & 1u); ++i) {
-    acc = acc + B[i];
-    __syncwarp();
-    if (lane == 0) B[i] = acc;
-  }
-  for (; i + 32 <= S; i += 32) {
-    double mine = 0.0;
+  // phase A: B[i] <- w_i = α_i·n_i for every i >= from.  α lives in global memory (L2 latency with
+  // the shared-memory carve-out this kernel uses), so sixteen loads per lane are put in flight at once and the lines are asked to stay in L1.
+  const uint32_t sB = X.sB, sLen = X.sLen;
+  SUB_T0();
+  for (uint32_t base = from; base < S; base += 512u) {
+    double a[16];
 #pragma unroll
-    for (uint32_t l = 0; l < 32u; l += 2) {
-      double2 ww = *reinterpret_cast<const double2*>(B + i + l);
-      acc = acc + ww.x;
-      if ((uint32_t)lane == l) mine = acc;
-      acc = acc + ww.y;
-      if ((uint32_t)lane == l + 1) mine = acc;
+    for (uint32_t k = 0; k < 16u; ++k) {
+      const uint32_t i = base + k * 32u + (uint32_t)lane;
+      a[k] = 0.0;
+      if (i < S) a[k] = ldg_keep_f64(alpha + i);
     }
-    __syncwarp();
-    B[i + lane] = mine;
-    __syncwarp();
+#pragma unroll
+    for (uint32_t k = 0; k < 16u; ++k) {
+      const uint32_t i = base + k * 32u + (uint32_t)lane;
+      if (i < S) sts_f64(sB + i * 8u, a[k] * (double)lds_u32(sLen + i * 4u));  // :693
+    }
   }
-  for (; i < S; ++i) {
-    acc = acc + B[i];
-    __syncwarp();
-    if (lane == 0) B[i] = acc;
+  __syncwarp();
+  SUB_ADD(0);
+  // phase B: in-place sequential left fold (the reference's `sum`).  Every lane runs the chain
+  // (the total is needed warp-wide); lane 0 alone writes the prefixes back.  The warp is converged
+  // here, so a lane never reads an entry lane 0 has already overwritten: loads of a group are
+  // issued by the whole warp before lane 0's stores of that group.
+  double acc = from ? lds_f64(sB + (from - 1u) * 8u) : 0.0;  // 0.0 + w_0 == w_0 exactly
+  uint32_t i = from;
+  const bool writer = lane == 0;
+  if (i < S && (i & 1u)) {  // align the chain to 16 bytes
+    acc = acc + lds_f64(sB + i * 8u);
+    if (writer) sts_f64(sB + i * 8u, acc);
+    ++i;
   }
+  if (i < S) acc = fold_chain<true>(sB + i * 8u, S - i, acc, writer);
+  __syncwarp();
+  SUB_ADD(1);
   const double death = X.P->rate_death * (double)r.n;     // :696
   const double M = X.P->rate_migration * (double)r.n;     // :697
   const double bd = acc + death;
@@ -743,6 +815,7 @@ __device__ __forceinline__ void refold(Ctx<T>& X, Rep& r) {
   r.exact_valid = false;
   r.dirty_from = kNone;
   __syncwarp();
+  SUB_ADD(2);
 }
 
 // Exact prob_cum = cumsum(vcat(α_subpop ./ λ, death/λ, M/λ)) (:703-718) in Julia's
@@ -950,17 +1023,13 @@ __device__ __forceinline__ void batch_eval(Ctx<T>& X, Rep& r, bool force_exact, 
 // sequential t += dt over lanes 0..last of one sub-batch (:701).  The increments are staged in
 // shared memory so that the chain is nothing but dependent fp64 adds (broadcast loads, issued
 // ahead); through shuffles every step also paid the shuffle latency.
+__device__ __forceinline__ double time_chain_at(uint32_t sDt, double t, uint32_t last) {
+  return fold_chain<false>(sDt, last + 1u, t, false);
+}
 __device__ __forceinline__ double time_chain(uint32_t sDt, int lane, double t, double dt, uint32_t last) {
-  asm volatile("st.shared.f64 [%0], %1;" ::"r"(sDt + (uint32_t)lane * 8u), "d"(dt) : "memory");
+  sts_f64(sDt + (uint32_t)lane * 8u, dt);
   __syncwarp();
-  uint32_t l = 0;
-  for (; l + 4 <= last + 1; l += 4) {
-    double d0, d1, d2, d3;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(d0), "=d"(d1) : "r"(sDt + l * 8u) : "memory");
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(d2), "=d"(d3) : "r"(sDt + l * 8u + 16u) : "memory");
-    t = t + d0; t = t + d1; t = t + d2; t = t + d3;
-  }
-  for (; l <= last; ++l) t = t + lds_f64(sDt + l * 8u);
+  t = time_chain_at(sDt, t, last);
   __syncwarp();
   return t;
 }
@@ -1518,33 +1587,38 @@ __device__ __noinline__ SlowOut slow_scan(const Ctx<T>& X, const Rep& r, double 
 // mailbox lives in shared memory.  Results are identical by construction (same evaluation code,
 // same state) — the parity tests run with helpers active.
 // ---------------------------------------------------------------------------------------------
-struct HelpMail {
-  uint32_t req, ack;      // owner bumps req for every posted window; helper sets ack = req when done
-  uint32_t helper, done;  // a helper is attached; the owner has no work left
-  uint32_t S, n, search_top, stream;
-  unsigned long long it_base;  // the helper evaluates iterations it_base+1 .. it_base+32
-  double lambda, guard, theta;
+struct HelpRes {
+  uint32_t ack;                             // id of the last request this helper finished
   uint32_t usable, effm, cls, x, cell, pos;  // first state-changing lane of the helper's window
-  uint32_t pad[2];
+  uint32_t pad;
   double dt[32];
+};
+struct HelpMail {
+  uint32_t word;          // (request id << 8) | helpers asked; written last by the owner
+  uint32_t nhelp, done;   // helpers attached (only grows); the owner has no work left
+  uint32_t S, n, search_top, stream, pad;
+  unsigned long long it_base;  // helper h evaluates iterations it_base + 32(h+1) + 1 .. + 32
+  double lambda, guard, theta;
+  HelpRes res[kMaxHelp];
 };
 static_assert(sizeof(HelpMail) % 16 == 0, "mailbox keeps the 16-byte alignment of the smem slices");
 
 template <typename T>
-__device__ __noinline__ void helper_serve(Ctx<T> X, volatile HelpMail* M) {
+__device__ __noinline__ void helper_serve(Ctx<T> X, volatile HelpMail* M, const uint32_t h) {
   const int lane = X.lane;
-  uint32_t last = M->ack;
+  volatile HelpRes* R = &M->res[h];
   for (;;) {
-    uint32_t rq;
+    uint32_t w;
     for (;;) {
-      rq = M->req;
-      if (rq != last) break;
+      w = M->word;
+      // a request is this helper's iff it was counted (h < helpers asked) and is not yet acknowledged
+      if ((w & 0xFFu) > h && R->ack != (w >> 8)) break;
       if (M->done) return;
-      __nanosleep(40);
+      __nanosleep(20);
     }
     __threadfence_block();
     Rep r;
-    r.it = M->it_base; r.S = M->S; r.n = M->n;
+    r.it = M->it_base + 32ull * (h + 1u); r.S = M->S; r.n = M->n;
     r.lambda = M->lambda; r.guard = M->guard; r.theta = M->theta;
     X.search_top = M->search_top;
     X.key.stream = M->stream;
@@ -1567,13 +1641,13 @@ __device__ __noinline__ void helper_serve(Ctx<T> X, volatile HelpMail* M) {
       eff = eval_target(X, r, q, c, cell, valid, wd, pos);
     }
     const uint32_t effm = __ballot_sync(FULL, eff);
-    M->dt[lane] = dt;
-    if (effm && lane == __ffs(effm) - 1) { M->cls = c; M->x = x; M->cell = cell; M->pos = pos; }
-    if (lane == 0) { M->effm = effm; M->usable = anyunc ? 0u : 1u; }
+    R->dt[lane] = dt;
+    if (effm && lane == __ffs(effm) - 1) { R->cls = c; R->x = x; R->cell = cell; R->pos = pos; }
+    if (lane == 0) { R->effm = effm; R->usable = anyunc ? 0u : 1u; }
     __syncwarp();
     __threadfence_block();
-    if (lane == 0) M->ack = rq;
-    last = rq;
+    if (lane == 0) R->ack = w >> 8;
+    __syncwarp();
   }
 }
 
@@ -1603,12 +1677,31 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M) {
   const uint32_t wmask = width == 32 ? FULL : ((1u << width) - 1u);
   const uint32_t nv = A.g.nv;
   uint32_t Ucur = 1;  // sub-batches per speculative window (1, 2 or 4), adapted to the run length
-  bool prev_null = false;  // the previous window changed nothing: worth asking a helper for the next-but-one
   if (force_exact || width != 32u) M = nullptr;
+
+  // Times that end a fast window, kept in registers (they live in global memory): the next snapshot
+  // time, and the excision time the reference's index arithmetic is looking at (:813-838 method 1
+  // never advances it, :1062-1064 method 2 advances it every iteration up to the last entry).
+  const double Tf = P.Tf;
+  const uint64_t max_iter = P.max_iter;
+  const int n_bott = P.n_bott;
+  const bool tree_quirk = n_bott > 0 && !intent && P.method == JSB_METHOD_TREE;
+  const double kNever = __longlong_as_double(0x7ff0000000000000ll);  // +inf
+  double watch_snap = kNever, watch_tb = -1.0;
+  auto reload_watch = [&]() {
+    watch_snap = r.snap_idx < P.n_snap ? X.tsnap[r.snap_idx] : kNever;
+    watch_tb = -1.0;  // never inside (r.t, t1]: event times are positive
+    if (n_bott > 0) {
+      if (intent) { if (r.bott_id > 0) watch_tb = X.tb[r.bott_id - 1]; }
+      else if (P.method == JSB_METHOD_TREE) watch_tb = X.tb[n_bott - 1];
+      else watch_tb = X.tb[0];
+    }
+  };
+  reload_watch();
 
   PROF_DECL
   for (;;) {
-    if (!(r.t < P.Tf && r.n > 0)) {  // loop test :687-688
+    if (!(r.t < Tf && r.n > 0)) {  // loop test :687-688
       if (P.rate_death == 0.0 && r.n == nv) r.status = JSB_ST_NONTERMINATING;
       break;
     }
@@ -1618,18 +1711,23 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M) {
 #endif
     if (r.dirty_from != kNone) { refold(X, r); PROF_ADD(PH_REFOLD); }
 
-    // ---- ask an attached helper warp for the window after this one ----------------------------------
-    bool posted = false;
-    if (M && prev_null && M->helper != 0 && M->ack == M->req) {
-      if (lane == 0) {
-        M->S = r.S; M->n = r.n; M->search_top = X.search_top; M->stream = X.key.stream;
-        M->it_base = r.it + 32;
-        M->lambda = r.lambda; M->guard = r.guard; M->theta = r.theta;
-        __threadfence_block();
-        M->req = M->req + 1;
+    // ---- ask the attached helper warps for the windows after this one ---------------------------
+    uint32_t nposted = 0, reqid = 0;
+    if (M) {
+      if (lane == 0) { nposted = M->nhelp; reqid = ((M->word >> 8) + 1u) & 0xFFFFFFu; }
+      nposted = __shfl_sync(FULL, nposted, 0);
+      reqid = __shfl_sync(FULL, reqid, 0);
+      if (nposted) {
+        if (nposted > (uint32_t)kMaxHelp) nposted = (uint32_t)kMaxHelp;
+        if (lane == 0) {
+          M->S = r.S; M->n = r.n; M->search_top = X.search_top; M->stream = X.key.stream;
+          M->it_base = r.it;
+          M->lambda = r.lambda; M->guard = r.guard; M->theta = r.theta;
+          __threadfence_block();  // the state written by the last event and this request, before the word
+          M->word = (reqid << 8) | nposted;
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      posted = true;
     }
 
     // ---- speculative window: Ucur sub-batches of 32 iterations ----------------------------------
@@ -1655,19 +1753,11 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M) {
 
     // ---- can anything other than that one event happen in (t, tend]? ---------------------------
     auto touches = [&](double t1, uint64_t n_commit) -> bool {
-      bool sl = !(t1 < P.Tf);
-      if (P.max_iter && r.it + n_commit > P.max_iter) sl = true;
-      if (r.snap_idx < P.n_snap && t1 > X.tsnap[r.snap_idx]) sl = true;
-      if (P.n_bott > 0) {
-        if (intent) {
-          if (r.bott_id > 0) { double tb = X.tb[r.bott_id - 1]; if (tb > r.t && tb <= t1) sl = true; }
-        } else if (P.method == JSB_METHOD_TREE) {
-          if (r.it + 1 < (uint64_t)P.n_bott) sl = true;
-          else { double tb = X.tb[P.n_bott - 1]; if (tb > r.t && tb <= t1) sl = true; }
-        } else {
-          double tb = X.tb[0]; if (tb > r.t && tb <= t1) sl = true;
-        }
-      }
+      bool sl = !(t1 < Tf);
+      if (max_iter && r.it + n_commit > max_iter) sl = true;
+      if (t1 > watch_snap) sl = true;
+      if (tree_quirk && r.it + 1 < (uint64_t)n_bott) sl = true;
+      if (watch_tb > r.t && watch_tb <= t1) sl = true;
       return sl;
     };
     bool slow = touches(tend, (uint64_t)ustar * 32u + jE + 1u);
@@ -1688,28 +1778,31 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M) {
     bool do_event = found;
     bool do_snap = false, do_bott = false;
     double tb_fire = 0.0, ratio_fire = 0.0;
-    bool from_helper = false;
+    int from_helper = -1;
 
-    if (posted) {
-      // the helper must be finished before anything changes (it reads the lists) and before its
-      // window is used; it has been running in parallel with this warp's own evaluation
-      while (M->ack != M->req) __nanosleep(20);
+    if (nposted) {
+      // every helper must be finished before anything changes (they read the lists) and before a
+      // window is used; they have been running in parallel with this warp's own evaluation
+      for (uint32_t h = 0; h < nposted; ++h)
+        while (M->res[h].ack != reqid) __nanosleep(20);
       __threadfence_block();
-      if (!found && !slow && M->usable) {
-        const uint32_t effm2 = M->effm;
+      uint64_t adv = 0;  // full null windows committed ahead of the one that ends the round
+      for (uint32_t h = 0; h < nposted && !found && !slow; ++h) {
+        volatile HelpRes* R = &M->res[h];
+        if (!R->usable) break;
+        const uint32_t effm2 = R->effm;
         const uint32_t jE2 = effm2 ? (uint32_t)__ffs(effm2) - 1u : 31u;
-        const double tend2 = time_chain(X.sDt, lane, tend, M->dt[lane], jE2);
-        if (!touches(tend2, 32u + jE2 + 1u)) {  // nothing but that one event inside the second window either
-          r.it += 32u;
-          tend = tend2;
-          j = jE = jE2;
-          ustar = 0;
-          found = do_event = effm2 != 0;
-          from_helper = true;
-        }
+        const double tend2 = time_chain_at(smem_addr(const_cast<double*>(&R->dt[0])), tend, jE2);
+        if (touches(tend2, adv + 32u + jE2 + 1u)) break;  // something besides that one event: redo it the slow way
+        adv += 32u;
+        tend = tend2;
+        j = jE = jE2;
+        ustar = 0;
+        found = do_event = effm2 != 0;
+        from_helper = (int)h;
       }
+      r.it += adv;
     }
-    prev_null = !found && !slow;
 
     if (!slow) {
       r.it += (uint64_t)ustar * 32u + jE + 1u;
@@ -1744,15 +1837,16 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M) {
         A.snaps[(size_t)X.local_idx * A.max_snap + r.snap_idx] = s;
       }
       r.snap_idx++;
+      reload_watch();
     }
     bool keep_going = true;
     if (do_event) {
       Eval ej;
       ej.cls = ej.x = ej.cell = ej.pos = 0;
-      if (from_helper) { ej.cls = M->cls; ej.x = M->x; ej.cell = M->cell; ej.pos = M->pos; }
+      if (from_helper >= 0) { volatile HelpRes* R = &M->res[from_helper]; ej.cls = R->cls; ej.x = R->x; ej.cell = R->cell; ej.pos = R->pos; }
 #pragma unroll
       for (int u = 0; u < kMaxSub; ++u)
-        if (!from_helper && (uint32_t)u == ustar) {
+        if (from_helper < 0 && (uint32_t)u == ustar) {
           ej.cls = __shfl_sync(FULL, cls[u], (int)j);
           ej.x = __shfl_sync(FULL, xx[u], (int)j);
           ej.cell = __shfl_sync(FULL, cell[u], (int)j);
@@ -1769,14 +1863,15 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M) {
     if (do_bott) {
       { Ctx<T> xc = X; Rep rc = r; apply_excision(xc, rc, tb_fire, ratio_fire); r = rc; }
       PROF_ADD(PH_EXC);
-      if (intent) r.bott_id = (r.bott_id < P.n_bott) ? r.bott_id + 1 : 0;
+      if (intent) { r.bott_id = (r.bott_id < P.n_bott) ? r.bott_id + 1 : 0; reload_watch(); }
     }
     if (r.status == JSB_ST_INTERNAL) break;
   }
 #ifdef JSB_PROFILE
   if (lane == 0 && (X.local_idx < 2 || r.it > 6000000ull)) {
-    printf("rep %lld it %llu S %u n %u | refold %lld/%lld (elems %lld) draws %lld/%lld class %lld eval %lld time %lld | birth %lld/%lld death %lld/%lld migr %lld/%lld exc %lld\n",
-           (long long)X.local_idx, (unsigned long long)r.it, r.S, r.n, prof_c[PH_REFOLD], prof_n[PH_REFOLD], prof_fold,
+    printf("sub-phases: refold A %lld B %lld tail %lld\n", g_sub[0], g_sub[1], g_sub[2]);
+    printf("rep %lld it %llu rounds %lld eff %u S %u n %u | refold %lld/%lld (elems %lld) draws %lld/%lld class %lld eval %lld time %lld | birth %lld/%lld death %lld/%lld migr %lld/%lld exc %lld\n",
+           (long long)X.local_idx, (unsigned long long)r.it, prof_n[PH_EVAL], r.n_eff, r.S, r.n, prof_c[PH_REFOLD], prof_n[PH_REFOLD], prof_fold,
            prof_c[PH_DRAWS], prof_n[PH_DRAWS], prof_c[PH_CLASS], prof_c[PH_EVAL], prof_c[PH_TIME], prof_c[PH_BIRTH],
            prof_n[PH_BIRTH], prof_c[PH_DEATH], prof_n[PH_DEATH], prof_c[PH_MIGR], prof_n[PH_MIGR], prof_c[PH_EXC]);
   }
@@ -1854,7 +1949,10 @@ __global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __
   DevPoint* sP;
   Ctx<T> X = make_ctx<T>(A, s_dyn, warp, lane, &sP);
   volatile HelpMail* myM = mail_of(s_dyn, A.smem_per_warp, warp);
-  if (lane == 0) { myM->req = 0; myM->ack = 0; myM->helper = 0; myM->done = 0; }
+  if (lane == 0) {
+    myM->word = 0; myM->nhelp = 0; myM->done = 0;
+    for (int h = 0; h < kMaxHelp; ++h) myM->res[h].ack = 0;
+  }
   __syncthreads();  // the only block-wide barrier: mailboxes are initialised before anyone looks
 
   for (uint32_t round = 0;; ++round) {
@@ -1888,29 +1986,50 @@ __global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __
     X.node_rate = A.dpool + P->rate_off;
     X.edge_parent = A.ipool + P->edge_off;
     X.edge_child = X.edge_parent + P->n_edges;
+    unsigned long long t_start = 0;
+    if (A.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
     run_replicate<T>(X, A.helpers ? myM : nullptr);
+    if (A.trace && lane == 0) {
+      unsigned long long t_end;
+      uint32_t smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long* tr = A.trace + 4ull * idx;
+      tr[0] = t_start; tr[1] = t_end; tr[2] = ((unsigned long long)smid << 8) | (unsigned)warp;
+      tr[3] = A.summaries[idx].n_iterations;
+    }
   }
 
   if (!A.helpers) return;
-  // no replicate left for this warp: help the busy warps of the block, one at a time
+  // no replicate left for this warp: help the busy warp of the block that has the fewest helpers
   if (lane == 0) myM->done = 1;
   __threadfence_block();
   __syncwarp();
   for (;;) {
     int target = -1;
-    for (int w = 0; w < nwarps && target < 0; ++w) {
-      if (w == warp) continue;
-      volatile HelpMail* m = mail_of(s_dyn, A.smem_per_warp, w);
-      if (m->done || m->helper) continue;
-      uint32_t got = 0;
-      if (lane == 0) got = atomicCAS(const_cast<uint32_t*>(&m->helper), 0u, 1u) == 0u ? 1u : 0u;
-      got = __shfl_sync(FULL, got, 0);
-      if (got) target = w;
+    uint32_t hidx = 0;
+    if (lane == 0) {
+      while (target < 0) {
+        int best = -1;
+        uint32_t best_n = (uint32_t)kMaxHelp;
+        for (int w = 0; w < nwarps; ++w) {
+          if (w == warp) continue;
+          volatile HelpMail* m = mail_of(s_dyn, A.smem_per_warp, w);
+          if (m->done) continue;
+          const uint32_t nh = m->nhelp;
+          if (nh < best_n) { best_n = nh; best = w; }
+        }
+        if (best < 0) break;
+        volatile HelpMail* m = mail_of(s_dyn, A.smem_per_warp, best);
+        if (atomicCAS(const_cast<uint32_t*>(&m->nhelp), best_n, best_n + 1u) == best_n) { target = best; hidx = best_n; }
+      }
     }
+    target = __shfl_sync(FULL, target, 0);
+    hidx = __shfl_sync(FULL, hidx, 0);
     if (target < 0) break;
     DevPoint* oP;
     Ctx<T> XO = make_ctx<T>(A, s_dyn, target, lane, &oP);
-    helper_serve<T>(XO, mail_of(s_dyn, A.smem_per_warp, target));
+    helper_serve<T>(XO, mail_of(s_dyn, A.smem_per_warp, target), hidx);
   }
 }
 
