@@ -617,11 +617,12 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     a.g.nv = (uint32_t)g->nv;
     a.site_bytes = g->nv <= 65536 ? 2u : 4u;
     const bool fast_mode = (opts->flags & JSB_MODE_REJECTION_FREE) != 0;
-    int wpb = 1;
+    int wpb = 1, wpb_max = 1;
     if ((fast_mode ? fast_prepare(a, opts->warps_per_sm, &wpb) : ssa_prepare(a, opts->warps_per_sm, &wpb)) != 0) { rc = fail(JSB_ECUDA, "cannot configure shared memory for the SSA kernel"); goto done; }
     // one block per SM; spread small ensembles over all SMs before stacking warps.  In the exact
     // mode warps without a replicate help the busy warps of their block (lookahead windows), so a
     // small ensemble still gets up to 1 + kMaxHelp warps per replicate.
+    wpb_max = wpb;
     const bool helpers = !fast_mode && !std::getenv("JSB_NO_HELPERS");
     int grid;
     {
@@ -634,8 +635,15 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
         if ((1 + kMaxHelp) * per_sm < wpb) wpb = (int)((1 + kMaxHelp) * per_sm);
         grid = (int)std::min<int64_t>(n_local, sms);
         a.static_map = (uint64_t)n_local < (uint64_t)grid * wpb ? 1u : 0u;
-        a.helpers = 1;
+        a.clock_max_busy = 1;
+        if (const char* e = std::getenv("JSB_CLOCK_MAX_BUSY")) a.clock_max_busy = (uint32_t)std::atoi(e);  // tuning hook
+        a.helpers = std::getenv("JSB_NO_CLOCK") ? 3u : 1u;  // bit 1: lookahead only, no decoupled clock helper (debug)
       }
+    }
+    if (const char* e = std::getenv("JSB_DEBUG_GRID")) {  // debug: pack the replicates on fewer SMs (contention measurements)
+      grid = std::max(1, std::atoi(e));
+      wpb = (int)std::min<int64_t>(wpb_max, (n_local + grid - 1) / grid);
+      a.static_map = 0;
     }
     const uint64_t slots = (uint64_t)grid * wpb;
 
@@ -711,11 +719,13 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
     CUDA_TRY(cudaEventRecord(ev0, stream));
-    // Optional longest-first scheduling (JSB_PILOT=1): a short pilot pass (8192 iterations per
-    // replicate; its work estimate has rank correlation ~0.97 with the final iteration counts)
-    // orders the full pass longest first.  Off by default: on the C2 ensemble the kernel time is
-    // the latency of the single heaviest replicate (measured: 2.82 s with, 2.76 s without).
-    if (!fast_mode && (uint64_t)n_local > slots && (uint64_t)n_local <= 16 * slots && std::getenv("JSB_PILOT")) {
+    // Longest-first scheduling for ensembles of a few replicates per warp slot: a short pilot pass (8192
+    // iterations per replicate; its work estimate has rank correlation ~0.97 with the final iteration
+    // counts) orders the full pass longest first, and the kernel deals the heaviest replicates out one
+    // per SM.  The kernel time is bounded by the latency of the heaviest replicates, so they must start
+    // first and must not share an SM (measured on the C2 ensemble: 2.4-2.7 s -> 2.1-2.2 s, pilot
+    // included; without the spreading the order alone gained nothing).  JSB_NO_PILOT=1 disables it.
+    if (!fast_mode && (uint64_t)n_local > slots && (uint64_t)n_local <= 16 * slots && !std::getenv("JSB_NO_PILOT")) {
       CUDA_TRY(cudaMalloc(&d_prio, sizeof(float) * n_local));
       CUDA_TRY(cudaMalloc(&d_order, sizeof(uint32_t) * n_local));
       RunArgs pa = a;
@@ -735,8 +745,11 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
       for (int64_t i = 0; i < n_local; ++i) order[i] = (uint32_t)i;
       std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return prio[x] > prio[y]; });
       CUDA_TRY(cudaMemcpyAsync(d_order, order.data(), sizeof(uint32_t) * n_local, cudaMemcpyHostToDevice, stream));
-      CUDA_TRY(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long), stream));
-      CUDA_TRY(cudaStreamSynchronize(stream));  // `order` is a host temporary
+      {  // the first grid*wpb ranks are dealt out statically by the kernel; the counter serves the rest
+        const unsigned long long first = slots;
+        CUDA_TRY(cudaMemcpyAsync(d_counters, &first, sizeof first, cudaMemcpyHostToDevice, stream));
+      }
+      CUDA_TRY(cudaStreamSynchronize(stream));  // `order` and `first` are host temporaries
       a.order = d_order;
     }
     {
