@@ -66,6 +66,11 @@ extern "C" {
  * from scratch and compare with the incrementally maintained tree (status JSB_ST_INTERNAL on a
  * mismatch).                                                                                 */
 #define JSB_QUIRK_DEBUG_VERIFY_TREE 0x800u
+/* Test hook for the decoupled mode of the exact kernel: hand the exact fold and
+ * time chain to a helper warp whenever one is available, also for replicates with few clones
+ * (by default only replicates with >= 64 clones do, below that it does not pay).  Results must
+ * be identical.                                                                               */
+#define JSB_QUIRK_DEBUG_DECOUPLE 0x1000u
 
 /* ---- output selection (jsb_run_opts.flags) -------------------------------------------- */
 #define JSB_OUT_EVENTS 0x1u  /* keep the per-replicate event log (`df`)                   */

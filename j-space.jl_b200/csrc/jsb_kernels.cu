@@ -1617,6 +1617,7 @@ struct ClockMsg {
 };
 static_assert(sizeof(ClockMsg) == 80, "ring slots are 16-byte multiples");
 constexpr uint32_t kClockRing = 8;
+constexpr uint32_t kDecMinClones = 64;   // below this the exact fold is cheaper than the hand-off (measured)
 constexpr uint32_t kClockResync = 1024;  // events between two exact re-bases of the owner's approximate table
 struct HelpMail {
   uint32_t word;          // (request id << 8) | helpers asked; written last by the owner
@@ -2103,6 +2104,7 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, c
   reload_watch();
 
   const bool dec_allowed = M != nullptr && (A.helpers & 2u) == 0 && A.pilot_iters == 0;
+  const uint32_t dec_min_clones = (P.quirks & JSB_QUIRK_DEBUG_DECOUPLE) ? 1u : kDecMinClones;
   uint64_t dec_hold = 0;  // no (re-)entry into decoupled mode before this iteration
 
   PROF_DECL
@@ -2120,7 +2122,8 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, c
     if (r.dirty_from != kNone) { refold(X, r); PROF_ADD(PH_REFOLD); }
 
     // ---- a clock helper is attached: run on the approximate clock until something needs the exact one
-    if (dec_allowed && r.it >= dec_hold && M->clk.attached != 0 && !(tree_quirk && r.it + 1 < (uint64_t)n_bott) &&
+    if (dec_allowed && r.S >= dec_min_clones && r.it >= dec_hold && M->clk.attached != 0 &&
+        !(tree_quirk && r.it + 1 < (uint64_t)n_bott) &&
         !(max_iter && r.it + 4096u >= max_iter)) {
       want_dec = true;  // handled outside this loop: the call must not shape its register allocation
       break;

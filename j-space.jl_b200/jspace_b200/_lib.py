@@ -26,6 +26,7 @@ QUIRK_DEBUG_SERIAL = 0x100
 QUIRK_DEBUG_EXACT_CLASSES = 0x200
 QUIRK_DEBUG_WIDE_GUARD = 0x400
 QUIRK_DEBUG_VERIFY_TREE = 0x800
+QUIRK_DEBUG_DECOUPLE = 0x1000
 OUT_EVENTS, OUT_LATTICE, OUT_LISTS = 0x1, 0x2, 0x4
 MODE_REJECTION_FREE = 0x100
 EV_DUPLICATE, EV_MUTATION, EV_DEATH, EV_MIGRATION = 0, 1, 2, 3

@@ -53,6 +53,37 @@ def test_class_selection_fallback_paths(jsb, oracle, flag):
     compare_runs(jsb, oracle, ("lattice", 2, 40, 40), p, reps=1)
 
 
+def test_decoupled_clock_helper_paths(jsb, oracle):
+    # JSB_QUIRK_DEBUG_DECOUPLE: the exact fold and time chain run on a helper warp one round behind
+    # the replicate, which works on an approximate table/clock (by default only with >= 64 clones);
+    # event times, fitness values and every decision must not change.  Covers displacement (voter
+    # rules), driver births, the driver tree, excisions and snapshots (exact-clock hand-backs),
+    # extinction, and a run long enough for the periodic re-base of the approximate table.
+    from jspace_b200 import _lib as L
+    q = L.QUIRK_DEBUG_DECOUPLE
+    compare_runs(jsb, oracle, ("lattice", 2, 40, 40), dict(DEFAULT, quirk_flags=q), reps=8)
+    for rule in ("voter", "hvoter", "anything-else"):
+        compare_runs(jsb, oracle, ("lattice", 2, 24, 24), dict(DEFAULT, rule=rule, Tf=40.0, mu_driver=0.05, quirk_flags=q), reps=6)
+    compare_runs(jsb, oracle, ("lattice", 3, 30, 30), dict(TREE, rule="hvoter", t_bottleneck=[40.0], ratio_bottleneck=[0.8],
+                                                          quirk_flags=q), reps=4)
+    compare_runs(jsb, oracle, ("lattice", 2, 32, 32), dict(DEFAULT, Tf=70.0, t_bottleneck=[30.0, 50.0], ratio_bottleneck=[0.5, 0.9],
+                                                          t_snapshot=[10.0, 35.0, 69.0], quirk_flags=q | L.QUIRK_EXCISION_INTENT), reps=3)
+    compare_runs(jsb, oracle, ("lattice", 2, 30, 30), dict(DEFAULT, Tf=60.0, rate_death=0.15, quirk_flags=q), reps=6)  # extinctions
+    compare_runs(jsb, oracle, ("lattice", 2, 12, 12), dict(DEFAULT, max_iterations=5000, quirk_flags=q), reps=4)
+    p = dict(DEFAULT, Tf=130.0, mu_driver=0.2, adv_mean=0.02, adv_std=0.01, quirk_flags=q)  # many clones, > 1024 events
+    compare_runs(jsb, oracle, ("lattice", 2, 40, 40), p, reps=2)
+    compare_runs(jsb, oracle, ("lattice", 2, 40, 40), dict(p, quirk_flags=q | L.QUIRK_DEBUG_WIDE_GUARD), reps=1)  # constant hand-backs
+
+
+def test_helper_warps_do_not_change_results(jsb, oracle, monkeypatch):
+    # the same replicates with and without lookahead / clock helpers (JSB_NO_HELPERS, JSB_NO_CLOCK)
+    p = dict(DEFAULT, Tf=110.0, mu_driver=0.1)
+    for env in ("JSB_NO_HELPERS", "JSB_NO_CLOCK"):
+        monkeypatch.setenv(env, "1")
+        compare_runs(jsb, oracle, ("lattice", 2, 40, 40), p, reps=3)
+        monkeypatch.delenv(env)
+
+
 def test_large_lattice_uint32_sites(jsb, oracle):
     # nv > 65536 switches the ordered lists to 32-bit site ids
     p = dict(DEFAULT, Tf=45.0, rate_death=0.03, rate_migration=0.05)
