@@ -73,7 +73,7 @@ struct RunArgs {
   uint8_t* ws;
   uint64_t ws_stride;
   uint32_t arena_cap;  // entries
-  uint32_t site_bytes; // 2 when nv <= 65536, else 4 (storage type of the ordered lists)
+  uint32_t site_bytes; // 2 when nv <= 65535, else 4 (storage type of the ordered lists and of the per-clone tables)
   uint32_t occ_words;  // per-warp shared occupancy bitmask words (0 = lattice too large, use global)
   uint32_t smem_per_warp;  // bytes of dynamic shared memory per warp
   WsLayout L;          // workspace offsets (computed once on the host)

@@ -230,11 +230,23 @@ __device__ __forceinline__ double fold_chain(uint32_t sa, uint32_t count, double
 #undef JSB_LOAD8
 #undef JSB_CHAIN8
 
+template <typename T>
+__device__ __forceinline__ uint32_t lds_tab(uint32_t base, uint32_t i);
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
   return v;
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return v;
+}
+// entry i of a per-clone table of site-typed values
+template <>
+__device__ __forceinline__ uint32_t lds_tab<uint16_t>(uint32_t base, uint32_t i) { return lds_u16(base + i * 2u); }
+template <>
+__device__ __forceinline__ uint32_t lds_tab<uint32_t>(uint32_t base, uint32_t i) { return lds_u32(base + i * 4u); }
 
 // ---------------------------------------------------------------------------------------------
 // Graph access (0-based vertices on the device; the ABI adds 1)
@@ -266,7 +278,7 @@ __device__ __forceinline__ uint32_t lattice_pick(const DevGraph& g, uint32_t v, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-replicate context.  T = storage type of the ordered lists (uint16_t when nv <= 65536).
+// Per-replicate context.  T = storage type of the ordered lists (uint16_t when nv <= 65535).
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 struct Ctx {
@@ -279,7 +291,13 @@ struct Ctx {
   T *Alist, *arena;
   uint16_t* a_head;         // tiered-vector segment heads of cs_alive
   uint32_t *inds, *samp;
-  uint32_t *c_off, *c_len;  // per-warp shared slices [kMaxClones]
+  T *c_off8, *c_len;        // per-warp shared slices [kTab]: arena offset / 8 and length of every clone's list,
+                            // stored in the site type (u16 lattices: 4 KB instead of 8 KB per warp)
+  __device__ __forceinline__ uint32_t off(uint32_t i) const { return (uint32_t)c_off8[i] << 3; }
+  __device__ __forceinline__ void set_off(uint32_t i, uint32_t v) {
+    if (v & 7u) __trap();  // blocks start on multiples of 8 entries (capacities are; compaction rounds to 8)
+    c_off8[i] = (T)(v >> 3);
+  }
   uint32_t* c_cap;          // global; capacities are powers of two >= kMinListCap
   double* c_alpha;
   uint16_t *c_parent, *c_label;
@@ -517,7 +535,7 @@ __device__ __noinline__ void arena_gc(Ctx<T>& X, Rep& r) {
   for (uint32_t step = 0; step < r.S; ++step) {
     uint32_t best = kNone, besti = kNone;
     for (uint32_t i = lane; i < r.S; i += 32) {
-      uint32_t o = X.c_off[i];
+      uint32_t o = X.off(i);
       if (!(X.c_cap[i] & 0x80000000u) && o < best) { best = o; besti = i; }
     }
     for (int d = 16; d > 0; d >>= 1) {
@@ -536,7 +554,7 @@ __device__ __noinline__ void arena_gc(Ctx<T>& X, Rep& r) {
       }
     }
     if (lane == 0) {
-      X.c_off[i] = top;
+      X.set_off(i, top);
       X.c_cap[i] = round_cap(l) | 0x80000000u;
     }
     __syncwarp();
@@ -556,7 +574,7 @@ __device__ __noinline__ void arena_gc(Ctx<T>& X, Rep& r) {
     // still-tagged block with the largest (squeezed offset, index)
     uint32_t best = 0, besti = kNone;
     for (uint32_t i = lane; i < r.S; i += 32) {
-      uint32_t o = X.c_off[i];
+      uint32_t o = X.off(i);
       if ((X.c_cap[i] & 0x80000000u) && (besti == kNone || o > best || (o == best && i > besti))) {
         best = o; besti = i;
       }
@@ -582,7 +600,7 @@ __device__ __noinline__ void arena_gc(Ctx<T>& X, Rep& r) {
       }
     }
     if (lane == 0) {
-      X.c_off[i] = noff;
+      X.set_off(i, noff);
       X.c_cap[i] = gc_cap(l);
     }
     __syncwarp();
@@ -674,14 +692,14 @@ __device__ __noinline__ bool list_grow(Ctx<T>& X, Rep& r, uint32_t c) {
     ncap = cap * 2;
     if (r.arena_top + ncap > X.A->arena_cap) { r.status = JSB_ST_INTERNAL; return false; }
   }
-  const uint32_t src = X.c_off[c], dst = r.arena_top;
+  const uint32_t src = X.off(c), dst = r.arena_top;
   for (uint32_t b = 0; b < len; b += 32) {
     uint32_t k = b + X.lane;
     if (k < len) X.arena[dst + k] = X.arena[src + k];
   }
   __syncwarp();
   if (X.lane == 0) {
-    X.c_off[c] = dst;
+    X.set_off(c, dst);
     X.c_cap[c] = ncap;
   }
   __syncwarp();
@@ -704,8 +722,8 @@ __device__ __forceinline__ bool list_append(Ctx<T>& X, Rep& r, uint32_t c, uint3
   }
   if (X.lane == 0) {
     uint32_t len = X.c_len[c];
-    X.arena[X.c_off[c] + len] = (T)site;
-    X.c_len[c] = len + 1;
+    X.arena[X.off(c) + len] = (T)site;
+    X.c_len[c] = (T)(len + 1);
   }
   __syncwarp();
   return true;
@@ -715,11 +733,11 @@ __device__ __forceinline__ bool list_append(Ctx<T>& X, Rep& r, uint32_t c, uint3
 template <typename T>
 __device__ __forceinline__ void list_remove_value(Ctx<T>& X, uint32_t c, uint32_t site) {
   uint32_t len = X.c_len[c];
-  T* list = X.arena + X.c_off[c];
+  T* list = X.arena + X.off(c);
   uint32_t idx = list_find<T>(list, len, site, X.lane);
   if (idx != kNone) {
     list_remove_at<T>(list, len, idx, X.lane);
-    if (X.lane == 0) X.c_len[c] = len - 1;
+    if (X.lane == 0) X.c_len[c] = (T)(len - 1);
     __syncwarp();
   }
 }
@@ -734,8 +752,8 @@ __device__ __noinline__ bool new_clone(Ctx<T>& X, Rep& r, uint32_t parent1, uint
     if (r.arena_top + kMinListCap > X.A->arena_cap) { r.status = JSB_ST_INTERNAL; return false; }
   }
   if (X.lane == 0) {
-    X.c_off[c] = r.arena_top;
-    X.c_len[c] = 1;
+    X.set_off(c, r.arena_top);
+    X.c_len[c] = (T)(1);
     X.c_cap[c] = kMinListCap;
     X.c_alpha[c] = alpha;
     X.c_parent[c] = (uint16_t)parent1;
@@ -760,7 +778,6 @@ __device__ __forceinline__ void refold(Ctx<T>& X, Rep& r) {
   const int lane = X.lane;
   double* __restrict__ B = X.B;
   const double* __restrict__ alpha = X.c_alpha;
-  const uint32_t* __restrict__ clen = X.c_len;
   // phase A: B[i] <- w_i = α_i·n_i for every i >= from.  α lives in global memory (L2 latency with
   // the shared-memory carve-out this kernel uses), so sixteen loads per lane are put in flight at once and the lines are asked to stay in L1.
   const uint32_t sB = X.sB, sLen = X.sLen;
@@ -776,7 +793,7 @@ __device__ __forceinline__ void refold(Ctx<T>& X, Rep& r) {
 #pragma unroll
     for (uint32_t k = 0; k < 16u; ++k) {
       const uint32_t i = base + k * 32u + (uint32_t)lane;
-      if (i < S) sts_f64(sB + i * 8u, a[k] * (double)lds_u32(sLen + i * 4u));  // :693
+      if (i < S) sts_f64(sB + i * 8u, a[k] * (double)lds_tab<T>(sLen, i));  // :693
     }
   }
   __syncwarp();
@@ -913,7 +930,7 @@ __device__ __forceinline__ void eval_member(const Ctx<T>& X, const Rep& r, uint6
   const uint32_t S = r.S;
   const bool is_birth = cls < S;
   const uint32_t ci = is_birth ? cls : 0u;
-  const uint32_t off = lds_u32(X.sOff + ci * 4u), cl = lds_u32(X.sLen + ci * 4u);
+  const uint32_t off = lds_tab<T>(X.sOff, ci) << 3, cl = lds_tab<T>(X.sLen, ci);
   const T* list = X.arena + off;
   const uint32_t llen = is_birth ? cl : r.n;
   // cls >= S+2: findfirst -> nothing in the reference; llen == 0: rand(1:0) throws.  Contract:
@@ -1353,7 +1370,7 @@ __device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double
   }
   for (uint32_t c = 0; c < r.S; ++c) {
     uint32_t len = X.c_len[c];
-    T* list = X.arena + X.c_off[c];
+    T* list = X.arena + X.off(c);
     uint32_t wpos = 0;
     for (uint32_t base = 0; base < len; base += 32) {
       uint32_t i = base + lane;
@@ -1365,7 +1382,7 @@ __device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double
       wpos += __popc(m);
       __syncwarp();
     }
-    if (lane == 0) X.c_len[c] = wpos;
+    if (lane == 0) X.c_len[c] = (T)(wpos);
   }
   __syncwarp();
   r.n = n - k;
@@ -1441,8 +1458,8 @@ __device__ __noinline__ void seed_replicate(Ctx<T>& X, Rep& r) {
     uint32_t cap = kMinListCap;
     while (cap < n0) cap *= 2;
     if (lane == 0) {
-      X.c_off[0] = 0;
-      X.c_len[0] = n0;
+      X.set_off(0, 0);
+      X.c_len[0] = (T)(n0);
       X.c_cap[0] = cap;
       X.c_alpha[0] = (P.method == JSB_METHOD_TREE) ? P.root_rate : P.rate_birth;  // :664 / :881
       X.c_parent[0] = 0;
@@ -1512,7 +1529,7 @@ __device__ __noinline__ void write_outputs(Ctx<T>& X, Rep& r) {
     uint32_t wpos = 0;
     for (uint32_t c = 0; c < r.S; ++c) {
       uint32_t len = X.c_len[c];
-      const T* list = X.arena + X.c_off[c];
+      const T* list = X.arena + X.off(c);
       for (uint32_t i = lane; i < len; i += 32) ll[wpos + i] = (uint32_t)list[i] + 1;
       wpos += len;
     }
@@ -1704,8 +1721,10 @@ __device__ __noinline__ void helper_serve(Ctx<T> X, volatile HelpMail* M, const 
 __device__ __forceinline__ unsigned char* slice_of(const double* my_B, int my_warp, uint32_t smem_per_warp, uint32_t warp) {
   return reinterpret_cast<unsigned char*>(const_cast<double*>(my_B)) + ((long)warp - (long)my_warp) * (long)smem_per_warp;
 }
-__device__ __forceinline__ volatile ClockMsg* ring_of(unsigned char* slice) {  // the helper's (idle) c_off region
-  return reinterpret_cast<volatile ClockMsg*>(slice + sizeof(double) * (kSmemTable + 32) + sizeof(uint32_t) * kTab);
+template <typename T>
+__device__ __forceinline__ volatile ClockMsg* ring_of(unsigned char* slice) {  // the helper's (idle) c_off8 region
+  static_assert(sizeof(T) * kTab >= sizeof(ClockMsg) * kClockRing, "the ring fits the region");
+  return reinterpret_cast<volatile ClockMsg*>(slice + sizeof(double) * (kSmemTable + 32) + sizeof(T) * kTab);
 }
 
 // XO: the owner's context; `mine`: this (idle) warp's own shared slice, reused as
@@ -1715,11 +1734,11 @@ __device__ __noinline__ void clock_serve(Ctx<T> XO, volatile HelpMail* M, unsign
   const int lane = XO.lane;
   const RunArgs& A = *XO.A;
   volatile ClockChan* C = &M->clk;
-  volatile ClockMsg* ring = ring_of(mine);
+  volatile ClockMsg* ring = ring_of<T>(mine);
   // the owner's context with the tables redirected to this warp's slice
   Ctx<T> XF = XO;
   XF.B = reinterpret_cast<double*>(mine);
-  XF.c_len = reinterpret_cast<uint32_t*>(mine + sizeof(double) * (kSmemTable + 32));
+  XF.c_len = reinterpret_cast<T*>(mine + sizeof(double) * (kSmemTable + 32));
   XF.sB = smem_addr(XF.B);
   XF.sDt = XF.sB + 8u * kSmemTable;
   XF.sLen = smem_addr(XF.c_len);
@@ -1739,7 +1758,7 @@ __device__ __noinline__ void clock_serve(Ctx<T> XO, volatile HelpMail* M, unsign
     const uint32_t kind = m->kind, S = m->S, n = m->n;
     if (kind == 0) {  // INIT: take over the owner's exact table, sizes, clock
       for (uint32_t i = lane; i < S + 2; i += 32) sts_f64(XF.sB + i * 8u, lds_f64(soB + i * 8u));
-      for (uint32_t i = lane; i < S; i += 32) XF.c_len[i] = lds_u32(soLen + i * 4u);
+      for (uint32_t i = lane; i < S; i += 32) XF.c_len[i] = (T)lds_tab<T>(soLen, i);
       t = C->t_init;
       lambda = C->lambda_init;
       theta = 1.0 / lambda;
@@ -1766,7 +1785,7 @@ __device__ __noinline__ void clock_serve(Ctx<T> XO, volatile HelpMail* M, unsign
           for (uint32_t u = 0; u < n_upd; ++u) {
             const uint32_t idx = m->upd_idx[u];
             const int k = m->upd_kind[u];
-            XF.c_len[idx] = k == 2 ? 1u : XF.c_len[idx] + (uint32_t)k;
+            XF.c_len[idx] = (T)(k == 2 ? 1u : (uint32_t)XF.c_len[idx] + (uint32_t)k);
           }
         }
         __syncwarp();
@@ -1900,7 +1919,7 @@ __device__ __noinline__ bool run_decoupled(Ctx<T>& Xref, Rep& rref, volatile Hel
   if (lane == 0) hw = M->clk.warp;
   hw = __shfl_sync(FULL, hw, 0);
   unsigned char* fh_slice = slice_of(X.B, my_warp, A.smem_per_warp, hw);
-  volatile ClockMsg* ring = ring_of(fh_slice);
+  volatile ClockMsg* ring = ring_of<T>(fh_slice);
   { Ctx<T> xc = X; Rep rc = r; dec_enter(xc, rc, M, ring); }
   r.guard = ((P.quirks & JSB_QUIRK_DEBUG_WIDE_GUARD) ? 1e-3 : 2.0 * kGuardEps) * r.lambda;
   uint32_t dec_events = 0;  // events since the approximate table was re-based on the exact one
@@ -2319,9 +2338,10 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, c
 }
 
 // Per-warp shared-memory slice:
-//   [ B: kSmemTable doubles | dt staging: 32 doubles | c_len: kTab u32 | c_off: kTab u32 | DevPoint | occupancy bits ]
-__host__ __device__ inline size_t smem_base_bytes() {
-  return sizeof(double) * (kSmemTable + 32) + 2 * sizeof(uint32_t) * kTab + ((sizeof(DevPoint) + 15) & ~size_t(15));
+//   [ B: kSmemTable doubles | dt staging: 32 doubles | c_len: kTab sites | c_off8: kTab sites | DevPoint | occupancy bits ]
+// ("site" = the u16/u32 storage type of the ordered lists)
+__host__ __device__ inline size_t smem_base_bytes(uint32_t site_bytes) {
+  return sizeof(double) * (kSmemTable + 32) + 2 * (size_t)site_bytes * kTab + ((sizeof(DevPoint) + 15) & ~size_t(15));
 }
 // the helper mailbox sits at the end of every warp's slice
 __device__ __forceinline__ volatile HelpMail* mail_of(unsigned char* s_dyn, uint32_t smem_per_warp, int warp) {
@@ -2352,15 +2372,18 @@ __device__ __forceinline__ Ctx<T> make_ctx(const RunArgs& A, unsigned char* s_dy
   X.g_w = reinterpret_cast<double*>(base + L.g_w);
   X.g_c = reinterpret_cast<double*>(base + L.g_c);
   X.B = reinterpret_cast<double*>(sw);
-  X.c_len = reinterpret_cast<uint32_t*>(sw + sizeof(double) * (kSmemTable + 32));
-  X.c_off = X.c_len + kTab;
-  DevPoint* sP = reinterpret_cast<DevPoint*>(X.c_off + kTab);
-  X.occ = A.occ_words ? reinterpret_cast<uint32_t*>(sw + smem_base_bytes()) : nullptr;
+  X.c_len = reinterpret_cast<T*>(sw + sizeof(double) * (kSmemTable + 32));
+  X.c_off8 = X.c_len + kTab;
+  DevPoint* sP = reinterpret_cast<DevPoint*>(X.c_off8 + kTab);
+  X.occ = A.occ_words ? reinterpret_cast<uint32_t*>(sw + smem_base_bytes((uint32_t)sizeof(T))) : nullptr;
   X.sB = smem_addr(X.B);
   X.sDt = X.sB + 8u * kSmemTable;
   X.sLen = smem_addr(X.c_len);
-  X.sOff = smem_addr(X.c_off);
+  X.sOff = smem_addr(X.c_off8);
   X.sOcc = X.occ ? smem_addr(X.occ) : 0u;
+  // opaque to the compiler from here on: otherwise ptxas re-derives the shared-window addresses (S2R
+  // SR_CgaCtaId + cvta, ~4 % of all issued instructions in the profile) wherever it is short of registers
+  asm volatile("" : "+r"(X.sB), "+r"(X.sDt), "+r"(X.sLen), "+r"(X.sOff), "+r"(X.sOcc));
   X.search_top = 2;
   X.key.k0 = (uint32_t)A.seed;
   X.key.k1 = (uint32_t)(A.seed >> 32);
@@ -2490,8 +2513,8 @@ int ssa_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block) {
   cudaGetDevice(&dev);
   int max_optin = 0;
   if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
-  const size_t with_occ = ((smem_base_bytes() + 4ull * words + 15) & ~size_t(15)) + sizeof(HelpMail);
-  const size_t without = ((smem_base_bytes() + 15) & ~size_t(15)) + sizeof(HelpMail);
+  const size_t with_occ = ((smem_base_bytes(args.site_bytes) + 4ull * words + 15) & ~size_t(15)) + sizeof(HelpMail);
+  const size_t without = ((smem_base_bytes(args.site_bytes) + 15) & ~size_t(15)) + sizeof(HelpMail);
   int cap = kMaxWarpsPerBlock;
   if (max_warps_per_sm > 0 && max_warps_per_sm < cap) cap = max_warps_per_sm;
   int w_occ = (int)((size_t)max_optin / with_occ);
