@@ -542,7 +542,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
   uint8_t* d_ws = nullptr;
   jsb_summary* d_sum = nullptr;
   jsb_clone* d_clones = nullptr;
-  unsigned long long* d_counters = nullptr;  // [0] work counter, [1] clone pool next
+  unsigned long long* d_counters = nullptr;  // [0] work counter, [1] clone pool next, [2] entries into decoupled mode
   long long* d_clone_off = nullptr;
   jsb_event *d_log = nullptr, *d_gather = nullptr;
   uint32_t* d_chunk_next = nullptr;
@@ -622,11 +622,20 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     // one block per SM; spread small ensembles over all SMs before stacking warps.  In the exact
     // mode warps without a replicate help the busy warps of their block (lookahead windows), so a
     // small ensemble still gets up to 1 + kMaxHelp warps per replicate.
-    // Twelve warps fit an SM for lattices up to 65 535 sites, and a throughput-bound sweep (many replicates
-    // per warp slot) gains ~8 % from them; an ensemble of a few replicates per slot is bound by the latency
-    // of its heaviest replicates, which run faster next to fewer neighbours (C2: 2.14-2.19 s at ten warps,
-    // 2.20-2.22 s at twelve).
-    if (!fast_mode && opts->warps_per_sm == 0 && wpb > 10 && (uint64_t)n_local <= 16ull * 10ull * (uint64_t)prop.multiProcessorCount) wpb = 10;
+    // How many warps per SM?  Shared memory and L1 share 256 KB and the carve-out comes in steps (..., 132,
+    // 164, 196, 228 KB); L1 caches the member lists (hit rate ~57 %), so fewer resident warps can be faster.
+    // Measured: a throughput-bound sweep (65 536 replicates of 100x100) wants every warp that fits (12: 5.65 s,
+    // 10: 5.89 s, 8: 5.98 s); an ensemble of a few replicates per warp slot is bound by the latency of its
+    // heaviest replicates and wants the 164 KB step (C2, 4096 x 200x200: 8 warps 1.96-1.98 s, 10 warps
+    // 2.06 s, 12 warps 2.20 s).
+    if (!fast_mode && opts->warps_per_sm == 0 && (uint64_t)n_local <= 16ull * 10ull * (uint64_t)prop.multiProcessorCount) {
+      const int w164 = (int)((164u * 1024u - 1024u) / a.smem_per_warp);
+      const int w196 = (int)((196u * 1024u - 1024u) / a.smem_per_warp);
+      const int want = w164 >= 6 ? w164 : (w196 >= 6 ? w196 : wpb);
+      if (want < wpb) {
+        if (ssa_prepare(a, want, &wpb) != 0) { rc = fail(JSB_ECUDA, "cannot configure shared memory for the SSA kernel"); goto done; }
+      }
+    }
     wpb_max = wpb;
     const bool helpers = !fast_mode && !std::getenv("JSB_NO_HELPERS");
     int grid;
@@ -663,8 +672,8 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
 
     // ---- outputs --------------------------------------------------------------------------
     CUDA_TRY(cudaMalloc(&d_sum, sizeof(jsb_summary) * n_local));
-    CUDA_TRY(cudaMalloc(&d_counters, sizeof(unsigned long long) * 2));
-    CUDA_TRY(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 2, stream));
+    CUDA_TRY(cudaMalloc(&d_counters, sizeof(unsigned long long) * 3));
+    CUDA_TRY(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 3, stream));
     unsigned long long clone_cap = std::min<unsigned long long>((unsigned long long)n_local * kMaxClones, 8ull << 20);
     CUDA_TRY(cudaMalloc(&d_clones, sizeof(jsb_clone) * clone_cap));
     CUDA_TRY(cudaMalloc(&d_clone_off, sizeof(long long) * n_local));
@@ -780,8 +789,9 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     res->summaries.resize((size_t)n_local);
     CUDA_TRY(cudaMemcpy(res->summaries.data(), d_sum, sizeof(jsb_summary) * n_local, cudaMemcpyDeviceToHost));
     {
-      unsigned long long counters[2];
+      unsigned long long counters[3];
       CUDA_TRY(cudaMemcpy(counters, d_counters, sizeof counters, cudaMemcpyDeviceToHost));
+      if (std::getenv("JSB_TIMING")) std::fprintf(stderr, "[jsb] entries into decoupled mode: %llu\n", counters[2]);
       unsigned long long used = std::min(counters[1], clone_cap);
       res->clones.resize((size_t)used);
       res->clone_off.resize((size_t)n_local);

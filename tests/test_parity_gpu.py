@@ -73,6 +73,11 @@ def test_decoupled_clock_helper_paths(jsb, oracle):
     p = dict(DEFAULT, Tf=130.0, mu_driver=0.2, adv_mean=0.02, adv_std=0.01, quirk_flags=q)  # many clones, > 1024 events
     compare_runs(jsb, oracle, ("lattice", 2, 40, 40), p, reps=2)
     compare_runs(jsb, oracle, ("lattice", 2, 40, 40), dict(p, quirk_flags=q | L.QUIRK_DEBUG_WIDE_GUARD), reps=1)  # constant hand-backs
+    # 32-bit site ids (nv > 65535) and a CSR graph
+    compare_runs(jsb, oracle, ("lattice", 2, 300, 300), dict(DEFAULT, Tf=45.0, rate_death=0.03, rate_migration=0.05, quirk_flags=q), reps=2)
+    from graphs import random_geometric_csr
+    rowptr, colidx = random_geometric_csr(3000, seed=4321)
+    compare_runs(jsb, oracle, ("csr", rowptr, colidx), dict(DEFAULT, Tf=80.0, quirk_flags=q), reps=3, candidates=[17])
 
 
 def test_helper_warps_do_not_change_results(jsb, oracle, monkeypatch):
