@@ -2538,7 +2538,8 @@ int ssa_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block) {
     // caches the member lists (hit rate ~57 %; every KB of carve-out taken from it was measurable)
     int sm_max = 0;
     cudaDeviceGetAttribute(&sm_max, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-    int pct = sm_max > 0 ? (int)(((long long)(bytes + 1024) * 100 + sm_max - 1) / sm_max) : 100;
+    // rounded down: the driver never goes below what the block needs, and rounding up can skip a step
+    int pct = sm_max > 0 ? (int)(((long long)(bytes + 1024) * 100) / sm_max) : 100;
     if (pct > 100) pct = 100;
     cudaFuncSetAttribute(ssa_kernel<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     cudaFuncSetAttribute(ssa_kernel<uint32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
