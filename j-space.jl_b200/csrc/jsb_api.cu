@@ -628,13 +628,14 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     // 10: 5.89 s, 8: 5.98 s); an ensemble of a few replicates per warp slot is bound by the latency of its
     // heaviest replicates and wants a small step (C2, 4096 x 200x200: 7 warps at 132 KB 1.92 s, 8 warps at
     // 164 KB 1.94-1.96 s, 6 warps 1.99 s, 10 warps at 196 KB 2.06 s, 12 warps at 228 KB 2.20 s).
-    if (!fast_mode && opts->warps_per_sm == 0 && (uint64_t)n_local <= 16ull * 10ull * (uint64_t)prop.multiProcessorCount) {
+    // The rejection-free kernel behaves the same way (C2: 12 warps 1.38 s, 8 warps 1.24 s, 7 warps 1.25 s).
+    if (opts->warps_per_sm == 0 && (uint64_t)n_local <= 16ull * 10ull * (uint64_t)prop.multiProcessorCount) {
       const int w132 = (int)((132u * 1024u - 1024u) / a.smem_per_warp);
       const int w164 = (int)((164u * 1024u - 1024u) / a.smem_per_warp);
       const int w196 = (int)((196u * 1024u - 1024u) / a.smem_per_warp);
       const int want = w132 >= 6 ? w132 : (w164 >= 6 ? w164 : (w196 >= 6 ? w196 : wpb));
       if (want < wpb) {
-        if (ssa_prepare(a, want, &wpb) != 0) { rc = fail(JSB_ECUDA, "cannot configure shared memory for the SSA kernel"); goto done; }
+        if ((fast_mode ? fast_prepare(a, want, &wpb) : ssa_prepare(a, want, &wpb)) != 0) { rc = fail(JSB_ECUDA, "cannot configure shared memory for the SSA kernel"); goto done; }
       }
     }
     wpb_max = wpb;

@@ -3481,6 +3481,13 @@ int fast_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block) {
   args.fast_smem_tree = smem_tree ? 1u : 0u;
   args.smem_per_warp = (uint32_t)per_warp;
   if (cudaFuncSetAttribute(fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * w)) != cudaSuccess) return -1;
+  {  // no more carve-out than needed: the rest of the 256 KB is L1 (see ssa_prepare)
+    int sm_max = 0;
+    cudaDeviceGetAttribute(&sm_max, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    int pct = sm_max > 0 ? (int)(((long long)(per_warp * w + 1024) * 100) / sm_max) : 100;
+    if (pct > 100) pct = 100;
+    cudaFuncSetAttribute(fast_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  }
   *warps_per_block = w;
   return 0;
 }
