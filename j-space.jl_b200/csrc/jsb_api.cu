@@ -652,6 +652,8 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
         grid = (int)std::min<int64_t>(n_local, sms);
         a.static_map = (uint64_t)n_local < (uint64_t)grid * wpb ? 1u : 0u;
         a.clock_max_busy = 3;
+        a.dec_min_clones = kDecMinClones;
+        if (const char* e = std::getenv("JSB_DEC_MIN_CLONES")) a.dec_min_clones = (uint32_t)std::max(1, std::atoi(e));  // tuning hook
         if (const char* e = std::getenv("JSB_CLOCK_MAX_BUSY")) a.clock_max_busy = (uint32_t)std::atoi(e);  // tuning hook
         a.helpers = std::getenv("JSB_NO_CLOCK") ? 3u : 1u;  // bit 1: lookahead only, no decoupled clock helper (debug)
       }

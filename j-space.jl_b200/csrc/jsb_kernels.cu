@@ -1634,7 +1634,6 @@ struct ClockMsg {
 };
 static_assert(sizeof(ClockMsg) == 80, "ring slots are 16-byte multiples");
 constexpr uint32_t kClockRing = 8;
-constexpr uint32_t kDecMinClones = 64;   // below this the exact fold is cheaper than the hand-off (measured)
 constexpr uint32_t kClockResync = 1024;  // events between two exact re-bases of the owner's approximate table
 struct HelpMail {
   uint32_t word;          // (request id << 8) | helpers asked; written last by the owner
@@ -2126,7 +2125,7 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, c
   reload_watch();
 
   const bool dec_allowed = M != nullptr && (A.helpers & 2u) == 0 && A.pilot_iters == 0;
-  const uint32_t dec_min_clones = (P.quirks & JSB_QUIRK_DEBUG_DECOUPLE) ? 1u : kDecMinClones;
+  const uint32_t dec_min_clones = (P.quirks & JSB_QUIRK_DEBUG_DECOUPLE) ? 1u : A.dec_min_clones;
   uint64_t dec_hold = 0;  // no (re-)entry into decoupled mode before this iteration
 
   PROF_DECL
