@@ -403,10 +403,18 @@ __device__ __forceinline__ void log_row(Ctx<T>& X, Rep& r, uint32_t type, uint32
                                         uint32_t parent, uint32_t site0, uint32_t site2_1, uint32_t clone,
                                         uint32_t label) {
   if (r.log_on) {
-    const uint32_t c = log_emit(X.A, X.local_idx, X.lane, r.nlog, r.cur_chunk, type, flags, time, cell, parent,
-                                site0 + 1, site2_1, clone, label);
-    if (c == kNone) { r.log_on = false; r.status = JSB_ST_LOG_OVERFLOW; }
-    else r.cur_chunk = c;
+    const uint32_t slot = (uint32_t)(r.nlog % kLogChunk);
+    if (slot != 0) {  // inside the current chunk: two 16-byte stores, no call
+      if (X.lane < 2) {
+        jsb_event* dst = X.A->log_pool + (size_t)r.cur_chunk * kLogChunk + slot;
+        log_store(dst, X.lane, time, cell, parent, site0 + 1, site2_1, clone, label, type, flags);
+      }
+    } else {          // first record of a chunk: claim one from the pool
+      const uint32_t c = log_emit(X.A, X.local_idx, X.lane, r.nlog, r.cur_chunk, type, flags, time, cell, parent,
+                                  site0 + 1, site2_1, clone, label);
+      if (c == kNone) { r.log_on = false; r.status = JSB_ST_LOG_OVERFLOW; }
+      else r.cur_chunk = c;
+    }
   }
   r.nlog++;
 }
@@ -2913,10 +2921,18 @@ __device__ __forceinline__ bool f_select(const FCtx& X, double target64, uint32_
 __device__ __forceinline__ void f_log(const FCtx& X, FRep& r, uint32_t type, uint32_t flags, double time, uint32_t cell,
                                       uint32_t parent, uint32_t site0, uint32_t site2_1, uint32_t clone, uint32_t label) {
   if (r.log_on) {
-    const uint32_t c = log_emit(X.A, X.local_idx, X.lane, r.nlog, r.cur_chunk, type, flags, time, cell, parent,
-                                site0 + 1, site2_1, clone, label);
-    if (c == kNone) { r.log_on = false; r.status = JSB_ST_LOG_OVERFLOW; }
-    else r.cur_chunk = c;
+    const uint32_t slot = (uint32_t)(r.nlog % kLogChunk);
+    if (slot != 0) {  // inside the current chunk: two 16-byte stores, no call
+      if (X.lane < 2) {
+        jsb_event* dst = X.A->log_pool + (size_t)r.cur_chunk * kLogChunk + slot;
+        log_store(dst, X.lane, time, cell, parent, site0 + 1, site2_1, clone, label, type, flags);
+      }
+    } else {          // first record of a chunk: claim one from the pool
+      const uint32_t c = log_emit(X.A, X.local_idx, X.lane, r.nlog, r.cur_chunk, type, flags, time, cell, parent,
+                                  site0 + 1, site2_1, clone, label);
+      if (c == kNone) { r.log_on = false; r.status = JSB_ST_LOG_OVERFLOW; }
+      else r.cur_chunk = c;
+    }
   }
   r.nlog++;
 }
