@@ -1607,13 +1607,14 @@ __device__ __noinline__ SlowOut slow_scan(const Ctx<T>& X, const Rep& r, double 
 
 // ---------------------------------------------------------------------------------------------
 // Warp-cooperative lookahead.  A warp that has no replicate left (the tail of an ensemble, or an
-// ensemble smaller than the machine) attaches to a busy warp of its block and evaluates the NEXT
-// window of 32 iterations for it, against the same state, while the owner evaluates the current
-// one.  If the owner's window turns out to be all null events it commits the helper's window too
-// (64 iterations per evaluation latency instead of 32).  The owner never changes any state while a
-// request is outstanding, and the helper only ever reads; both sit in the same block, so the
-// mailbox lives in shared memory.  Results are identical by construction (same evaluation code,
-// same state) — the parity tests run with helpers active.
+// ensemble smaller than the machine) attaches to a busy warp of its block; lookahead helper k
+// evaluates the window of 32 iterations k+1 windows ahead of the owner's, against the same state,
+// while the owner evaluates the current one.  The owner commits every window up to and including
+// the first one with a state-changing iteration (up to 160 iterations per evaluation latency
+// instead of 32).  The owner never changes any state while a request is outstanding, and the
+// helpers only ever read; all sit in the same block, so the mailbox lives in shared memory.
+// Results are identical by construction (same evaluation code, same state) — the parity tests run
+// with helpers active.
 // ---------------------------------------------------------------------------------------------
 struct HelpRes {
   uint32_t ack;                             // id of the last request this helper finished
