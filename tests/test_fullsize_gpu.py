@@ -68,6 +68,30 @@ def check_replicates(jsb, graph, point, reps, seed, seeds_of=None, n_check=2):
     return out
 
 
+def test_c2_helper_warps_leave_full_size_logs_untouched(jsb, monkeypatch):
+    """At full size the oracle is out of reach, but the plain exact loop (no helper warps) is the code the small
+    parity tests pin against it.  With 24 replicates on 148 SMs every replicate runs with lookahead helpers and,
+    once it has 64 clones, on the decoupled clock: the event logs (times bit for bit, patched into the records by
+    the clock helper) and the summaries must equal those of the plain loop."""
+    from jspace_b200 import _lib as L
+    g = jsb.Graph.lattice(200, 200, 2)
+    pt = jsb.Point(**DEFAULT, t_bottleneck=[50.0], ratio_bottleneck=[0.8], t_snapshot=[120.0])
+    a = jsb.run_ensemble(g, pt, 24, seed=1234, flags=L.OUT_EVENTS)
+    monkeypatch.setenv("JSB_NO_HELPERS", "1")
+    b = jsb.run_ensemble(g, pt, 24, seed=1234, flags=L.OUT_EVENTS)
+    monkeypatch.delenv("JSB_NO_HELPERS")
+    sa, sb = a.summaries, b.summaries
+    assert sa.tobytes() == sb.tobytes()
+    assert sa["n_clones"].max() > 300 and sa["n_iterations"].max() > 2e6
+    for i in np.argsort(-sa["n_events"].astype(np.int64))[:4].tolist():
+        ea, eb = a.events(i), b.events(i)
+        assert ea.tobytes() == eb.tobytes()
+        normal = ea[(ea["flags"] & 4) == 0]["time"]  # excised cells are logged at the excision time
+        assert np.all(np.diff(normal) >= 0) and normal[-1] <= sa["t_final"][i] <= 200.0 * (1 + 1e-12) + 1.0
+    a.close()
+    b.close()
+
+
 def test_c1_100x100_single_replicate_full(jsb):
     g = jsb.Graph.lattice(100, 100, 2)
     s = check_replicates(jsb, g, jsb.Point(**DEFAULT, t_bottleneck=[50.0], ratio_bottleneck=[0.8]), 4, 1234, n_check=4)
