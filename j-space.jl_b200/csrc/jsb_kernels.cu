@@ -2408,8 +2408,10 @@ __device__ __forceinline__ Ctx<T> make_ctx(const RunArgs& A, unsigned char* s_dy
   return X;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kMaxWarpsPerBlock * 32, 1) ssa_kernel(const __grid_constant__ RunArgs A) {
+// MAXT = largest block the instantiation is launched with.  Latency-bound ensembles run at most eight warps per
+// SM (see jsb_run), which leaves 255 registers per thread instead of 168: the 8-warp instantiation has no spills.
+template <typename T, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) ssa_kernel(const __grid_constant__ RunArgs A) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -2539,8 +2541,10 @@ int ssa_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block) {
   args.occ_words = use_occ ? words : 0;
   args.smem_per_warp = (uint32_t)(use_occ ? with_occ : without);
   const int bytes = (int)((size_t)args.smem_per_warp * w);
-  if (cudaFuncSetAttribute(ssa_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(ssa_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(ssa_kernel<uint16_t, kMaxWarpsPerBlock * 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(ssa_kernel<uint32_t, kMaxWarpsPerBlock * 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(ssa_kernel<uint16_t, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(ssa_kernel<uint32_t, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
   {
     // ask for no more shared-memory carve-out than the block needs: what is left of the 256 KB is the L1 that
     // caches the member lists (hit rate ~57 %; every KB of carve-out taken from it was measurable)
@@ -2549,8 +2553,10 @@ int ssa_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block) {
     // rounded down: the driver never goes below what the block needs, and rounding up can skip a step
     int pct = sm_max > 0 ? (int)(((long long)(bytes + 1024) * 100) / sm_max) : 100;
     if (pct > 100) pct = 100;
-    cudaFuncSetAttribute(ssa_kernel<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(ssa_kernel<uint32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(ssa_kernel<uint16_t, kMaxWarpsPerBlock * 32>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(ssa_kernel<uint32_t, kMaxWarpsPerBlock * 32>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(ssa_kernel<uint16_t, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(ssa_kernel<uint32_t, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
   }
   *warps_per_block = w;
   return 0;
@@ -2558,10 +2564,14 @@ int ssa_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block) {
 
 int launch_ssa(const RunArgs& args, int grid_blocks, int warps_per_block, void* stream) {
   const size_t smem = (size_t)args.smem_per_warp * warps_per_block;
-  if (args.site_bytes == 2)
-    ssa_kernel<uint16_t><<<grid_blocks, warps_per_block * 32, smem, (cudaStream_t)stream>>>(args);
-  else
-    ssa_kernel<uint32_t><<<grid_blocks, warps_per_block * 32, smem, (cudaStream_t)stream>>>(args);
+  const bool small_block = warps_per_block <= 8;
+  if (args.site_bytes == 2) {
+    if (small_block) ssa_kernel<uint16_t, 256><<<grid_blocks, warps_per_block * 32, smem, (cudaStream_t)stream>>>(args);
+    else ssa_kernel<uint16_t, kMaxWarpsPerBlock * 32><<<grid_blocks, warps_per_block * 32, smem, (cudaStream_t)stream>>>(args);
+  } else {
+    if (small_block) ssa_kernel<uint32_t, 256><<<grid_blocks, warps_per_block * 32, smem, (cudaStream_t)stream>>>(args);
+    else ssa_kernel<uint32_t, kMaxWarpsPerBlock * 32><<<grid_blocks, warps_per_block * 32, smem, (cudaStream_t)stream>>>(args);
+  }
   return (int)cudaGetLastError();
 }
 
@@ -3402,6 +3412,7 @@ __device__ __forceinline__ void f_run(const FCtx& X) {
   { FCtx xc = X; FRep rc = r; f_outputs(xc, rc); }
 }
 
+// (a 255-register instantiation for blocks of at most eight warps, as for ssa_kernel, changes nothing here: 1.26 s either way)
 __global__ void __launch_bounds__(384, 1) fast_kernel(const __grid_constant__ RunArgs A) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   const int lane = threadIdx.x & 31;
