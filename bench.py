@@ -47,9 +47,9 @@ BASE_SEED = 1234
 # algorithmic bytes per loop iteration, SURVEY.md §8(d)
 A_NULL, A_BIRTH, A_DEATH = 6.0, 78.0, 46.0
 # dram__bytes_read.sum + dram__bytes_write.sum of the main ssa_kernel launch of the timed step of workload C2
-# (4096 replicates), from the ncu pass committed as profiles/r1_bench_c2_launches.csv (launch ID 3: 55.56 GB read +
-# 41.30 GB written; the 29 ms pilot launch before it moves another 0.8 GB)
-MEASURED_TRAFFIC = {("C2", 4096): 96855636992}
+# (4096 replicates), from the ncu pass committed as profiles/r1_bench_c2_launches.csv (launch ID 3: 48.64 GB read +
+# 39.74 GB written; the 27 ms pilot launch before it moves another 0.8 GB)
+MEASURED_TRAFFIC = {("C2", 4096): 88381294336}
 
 
 def measured_peak_gbs():
