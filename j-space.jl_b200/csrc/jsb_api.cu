@@ -622,18 +622,21 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     // one block per SM; spread small ensembles over all SMs before stacking warps.  In the exact
     // mode warps without a replicate help the busy warps of their block (lookahead windows), so a
     // small ensemble still gets up to 1 + kMaxHelp warps per replicate.
-    // How many warps per SM?  Shared memory and L1 share 256 KB and the carve-out comes in steps (..., 132,
-    // 164, 196, 228 KB); L1 caches the member lists (hit rate ~57 %), so fewer resident warps can be faster.
-    // Measured: a throughput-bound sweep (65 536 replicates of 100x100) wants every warp that fits (12: 5.65 s,
-    // 10: 5.89 s, 8: 5.98 s); an ensemble of a few replicates per warp slot is bound by the latency of its
-    // heaviest replicates and wants a small step (C2, 4096 x 200x200: 7 warps at 132 KB 1.92 s, 8 warps at
-    // 164 KB 1.94-1.96 s, 6 warps 1.99 s, 10 warps at 196 KB 2.06 s, 12 warps at 228 KB 2.20 s).
-    // The rejection-free kernel behaves the same way (C2: 12 warps 1.38 s, 8 warps 1.24 s, 7 warps 1.25 s).
-    if (opts->warps_per_sm == 0 && (uint64_t)n_local <= 16ull * 10ull * (uint64_t)prop.multiProcessorCount) {
+    // How many warps per SM?  Two things favour few: shared memory and L1 share 256 KB and the carve-out comes
+    // in steps (..., 132, 164, 196, 228 KB), and L1 caches the member lists (hit rate 57 % at 60 KB, 91 % at
+    // 124 KB); and a block of at most eight warps may use 255 registers per thread instead of 168 (ssa_kernel's
+    // second instantiation: no spill traffic).  Measured, exact kernel: C2 (4096 x 200x200, latency-bound) 7
+    // warps/132 KB 1.74 s, 8 warps/164 KB 1.73 s, 6 warps 1.82 s, and with 168 registers 7 warps 1.92 s, 10
+    // warps/196 KB 2.06 s, 12 warps/228 KB 2.20 s; a throughput-bound sweep (65 536 replicates of 100x100) 8
+    // warps 5.37 s, 12 warps 5.63 s, 10 warps 5.80 s.  So: as many warps as fit the 132 KB step, at most eight.
+    // The rejection-free kernel was only measured on latency-bound ensembles (C2: 12 warps 1.38 s, 8 warps
+    // 1.24 s, 7 warps 1.25 s) and keeps every warp that fits for large sweeps.
+    if (opts->warps_per_sm == 0 && (!fast_mode || (uint64_t)n_local <= 16ull * 10ull * (uint64_t)prop.multiProcessorCount)) {
       const int w132 = (int)((132u * 1024u - 1024u) / a.smem_per_warp);
       const int w164 = (int)((164u * 1024u - 1024u) / a.smem_per_warp);
       const int w196 = (int)((196u * 1024u - 1024u) / a.smem_per_warp);
-      const int want = w132 >= 6 ? w132 : (w164 >= 6 ? w164 : (w196 >= 6 ? w196 : wpb));
+      int want = w132 >= 6 ? w132 : (w164 >= 6 ? w164 : (w196 >= 6 ? w196 : wpb));
+      if (!fast_mode && want > 8) want = 8;
       if (want < wpb) {
         if ((fast_mode ? fast_prepare(a, want, &wpb) : ssa_prepare(a, want, &wpb)) != 0) { rc = fail(JSB_ECUDA, "cannot configure shared memory for the SSA kernel"); goto done; }
       }
