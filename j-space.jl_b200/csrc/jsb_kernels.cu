@@ -265,16 +265,16 @@ __device__ __forceinline__ uint32_t lattice_mask(const DevGraph& g, uint32_t v) 
          ((uint32_t)(y + 1 < g.n2) << 4) | ((uint32_t)(z + 1 < g.n3) << 5);
 }
 __device__ __forceinline__ uint32_t lattice_pick(const DevGraph& g, uint32_t v, uint32_t mask, uint32_t j) {
-  int bit = 0;
+  // the j-th (0-based) set bit of mask (at most six bits are set; j < popc(mask))
+  uint32_t m = mask;
 #pragma unroll
-  for (int b = 0; b < 6; ++b) {
-    bool here = ((mask >> b) & 1u) && (__popc(mask & ((1u << b) - 1u)) == (int)j);
-    if (here) bit = b;
-  }
-  const int plane = (int)(g.n1 * g.n2);
-  const int n1 = (int)g.n1;
-  int delta = bit == 0 ? -plane : bit == 1 ? -n1 : bit == 2 ? -1 : bit == 3 ? 1 : bit == 4 ? n1 : plane;
-  return (uint32_t)((int)v + delta);
+  for (uint32_t k = 0; k < 5u; ++k)
+    if (k < j) m &= m - 1u;
+  const int bit = __ffs(m) - 1;
+  // bits 0..5 = -plane, -n1, -1, +1, +n1, +plane
+  const int dist = bit < 3 ? 2 - bit : bit - 3;  // 0: x, 1: y, 2: z
+  const int step = dist == 0 ? 1 : (dist == 1 ? (int)g.n1 : (int)(g.n1 * g.n2));
+  return (uint32_t)((int)v + (bit < 3 ? -step : step));
 }
 
 // ---------------------------------------------------------------------------------------------
