@@ -2435,7 +2435,9 @@ __global__ void __launch_bounds__(MAXT, 1) ssa_kernel(const __grid_constant__ Ru
     } else if (A.order && round == 0) {
       // longest-first order: the heaviest replicates are dealt out one per SM (rank k -> block k mod
       // grid), so that the long tails end up on different SMs; the work counter starts after them
-      idx = (unsigned long long)blockIdx.x + (unsigned long long)warp * gridDim.x;
+      // (boustrophedon: the SM that holds the heaviest replicate gets the lightest of every second row)
+      const unsigned b = (warp & 1) ? gridDim.x - 1u - blockIdx.x : blockIdx.x;
+      idx = (unsigned long long)b + (unsigned long long)warp * gridDim.x;
     } else {
       if (lane == 0) idx = atomicAdd(A.work_counter, 1ull);
       idx = __shfl_sync(FULL, idx, 0);
