@@ -50,6 +50,24 @@ def test_struct_layouts_match_the_header(jsb, tmp_path):
     assert got[2:7] == [32, 64, 16, 32, 24]
 
 
+def test_header_constants_match_the_python_mirror(jsb):
+    # every numeric #define JSB_* of the header has the same value in jspace_b200._lib (name without the prefix)
+    from jspace_b200 import _lib as L
+    txt = open(os.path.join(ROOT, "include", "jspace_b200.h")).read()
+    defs = {m.group(1): int(m.group(2), 0) for m in re.finditer(r"#define JSB_([A-Z0-9_]+)\s+\(?(-?(?:0x[0-9a-fA-F]+|\d+))u?\)?\s", txt)}
+    assert len(defs) >= 20
+    checked = 0
+    for name, val in defs.items():
+        if hasattr(L, name):
+            assert getattr(L, name) == val, name
+            checked += 1
+    for prefix in ("QUIRK_", "OUT_", "MODE_", "ST_"):
+        for name in defs:
+            if name.startswith(prefix):
+                assert hasattr(L, name), name
+    assert checked >= 15
+
+
 def test_graph_builders_match_oracle(jsb, oracle):
     for dim, row, col in [(2, 7, 5), (2, 100, 100), (3, 25, 25), (3, 350, 350), (5, 12, 12), (2, 1, 9)]:
         gj = jsb.Graph.lattice(row, col, dim)
