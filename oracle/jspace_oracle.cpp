@@ -343,6 +343,9 @@ struct Sim {
   uint64_t iter = 0;
   uint32_t next_id = 1;
   OrcSummary sum{};
+  // benchmark control (bench.py's time-boxed CPU arm): iterations done so far / stop request
+  volatile uint64_t* progress = nullptr;
+  volatile int* stop = nullptr;
 
   Sim(const Graph& g, const OrcParams& p, uint64_t seed, uint32_t stream, bool faithful)
       : G(g), P(p), rng{seed, stream}, faithful_scans(faithful) {
@@ -609,7 +612,9 @@ struct Sim {
         break;
       }
       if (P.max_iterations && iter >= P.max_iterations) { sum.status = ST_MAX_ITER; break; }
+      if (stop && *stop) { sum.status = ST_MAX_ITER; break; }
       ++iter;
+      if (progress) *progress = iter;
       const int S = (int)alpha.size();
       a_sub.resize(S);
       for (int i = 0; i < S; ++i) a_sub[i] = alpha[i] * (double)ca_subpop[i].size();  // :692-694
@@ -831,6 +836,21 @@ void* orc_run(void* g, const OrcParams* p, uint64_t seed, uint32_t stream, const
               int64_t n_candidates, int faithful_scans) {
   Graph* G = (Graph*)g;
   Sim* s = new Sim(*G, *p, seed, stream, faithful_scans != 0);
+  std::vector<int64_t> cand;
+  if (candidates) cand.assign(candidates, candidates + n_candidates);
+  if (!G->is_lattice && p->n_start_cells == 1 && cand.empty()) cand = closeness_argmax(*G);
+  s->seed_cells(cand);
+  s->run();
+  return s;
+}
+// Same, for bench.py's time-boxed CPU arm: *progress is updated every iteration, and the run stops
+// (status MAX_ITER, partial summary) as soon as *stop is non-zero.
+void* orc_run_ctl(void* g, const OrcParams* p, uint64_t seed, uint32_t stream, const int64_t* candidates,
+                  int64_t n_candidates, int faithful_scans, volatile uint64_t* progress, volatile int* stop) {
+  Graph* G = (Graph*)g;
+  Sim* s = new Sim(*G, *p, seed, stream, faithful_scans != 0);
+  s->progress = progress;
+  s->stop = stop;
   std::vector<int64_t> cand;
   if (candidates) cand.assign(candidates, candidates + n_candidates);
   if (!G->is_lattice && p->n_start_cells == 1 && cand.empty()) cand = closeness_argmax(*G);

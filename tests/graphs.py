@@ -2,9 +2,10 @@
 import numpy as np
 
 
-def random_geometric_csr(n, seed=4321, mean_degree=8.0):
+def random_geometric_csr(n, seed=4321, mean_degree=8.0, return_points=False):
     """n points uniform in the unit square, edge when distance < r, r = sqrt(mean_degree/(pi n)).
-    Returns (rowptr, colidx) of the largest connected component, 1-based ascending neighbours."""
+    Returns (rowptr, colidx) of the largest connected component, 1-based ascending neighbours
+    (and, with return_points, the coordinates of its vertices)."""
     rng = np.random.Generator(np.random.Philox(seed))
     pts = rng.random((n, 2))
     r = np.sqrt(mean_degree / (np.pi * n))
@@ -48,4 +49,12 @@ def random_geometric_csr(n, seed=4321, mean_degree=8.0):
     rowptr = np.zeros(nv + 1, dtype=np.int64)
     np.add.at(rowptr, s + 1, 1)
     rowptr = np.cumsum(rowptr)
+    if return_points:
+        return rowptr, (d + 1).astype(np.int32), pts[keep]
     return rowptr, (d + 1).astype(np.int32)
+
+
+def geometric_centre(pts):
+    """1-based vertex nearest to the middle of the unit square: the stand-in for the max-closeness vertex of
+    src/J_Space.jl:83-85 on graphs where the exact O(V*E) closeness is too slow to compute in a test."""
+    return int(np.argmin(((pts - 0.5) ** 2).sum(1))) + 1

@@ -22,22 +22,35 @@ def make_graphs(jsb, oracle, spec):
 
 
 def compare_runs(jsb, oracle, spec, params: dict, *, seed=1234, reps=1, g_begin=0, faithful=False,
-                 time_rtol=0.0, candidates=None, check_lists=True):
-    """Returns the list of oracle summaries; raises AssertionError on the first mismatch."""
+                 time_rtol=0.0, candidates=None, check_lists=True, only=None, warps_per_sm=0, log_pool_bytes=0,
+                 summaries_out=None):
+    """Returns the list of oracle summaries; raises AssertionError on the first mismatch.
+    `only`: local replicate indices to compare with the oracle (default: all of them) — the GPU
+    still runs the whole ensemble, so scheduling (pilot order, helpers, decoupled clock) is live."""
     from jspace_b200 import _lib as L
     gj, go = make_graphs(jsb, oracle, spec)
     if candidates is not None:
         gj.set_seed_candidates(candidates)
     flags = L.OUT_EVENTS | L.OUT_LATTICE | (L.OUT_LISTS if check_lists else 0)
-    point = jsb.Point(**params)
-    res = jsb.run_ensemble(gj, point, g_begin + reps, seed=seed, flags=flags, g_begin=g_begin,
-                           g_end=g_begin + reps)
+    # `params` may be a list of dicts = sweep points; then `reps` is the number of replicates PER POINT and
+    # replicate g = point * reps + r runs point g // reps (the library's global numbering)
+    plist = params if isinstance(params, (list, tuple)) else None
+    reps_per_point = reps if plist else g_begin + reps
+    if plist:
+        assert g_begin == 0
+        reps = reps * len(plist)
+    point = [jsb.Point(**q) for q in plist] if plist else jsb.Point(**params)
+    res = jsb.run_ensemble(gj, point, reps_per_point, seed=seed, flags=flags, g_begin=g_begin,
+                           g_end=g_begin + reps, warps_per_sm=warps_per_sm, log_pool_bytes=log_pool_bytes)
+    if summaries_out is not None:
+        summaries_out.append(res.summaries.copy())
     cand = candidates
     if cand is None and spec[0] != "lattice":
         cand = gj.seed_candidates()
     out = []
-    for i in range(res.count):
+    for i in (range(res.count) if only is None else only):
         stream = g_begin + i
+        params = plist[stream // reps_per_point] if plist else params
         orun = oracle.Run(go, oracle.make_params(**params), seed, stream, candidates=cand, faithful=faithful)
         s_gpu, s_cpu = res.summaries[i], orun.summary
         ctx = f"replicate {stream} params {params}"

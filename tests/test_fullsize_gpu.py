@@ -1,5 +1,6 @@
 """BASELINE.json's configurations at FULL size on the GPU, checked through size-independent
-properties (the oracle would take minutes to hours at these sizes):
+properties on MANY replicates (the direct bit-for-bit comparison with the oracle at these sizes is
+tests/test_fullsize_parity_gpu.py; the properties here cost nothing per replicate and do not need it):
   * replay round trip: applying the event log to the seeded lattice reproduces the final lattice,
     the clone table counts and n_alive (log -> state is the consumer's contract)
   * summary consistency and genealogy well-formedness
@@ -69,8 +70,7 @@ def check_replicates(jsb, graph, point, reps, seed, seeds_of=None, n_check=2):
 
 
 def test_c2_helper_warps_leave_full_size_logs_untouched(jsb, monkeypatch):
-    """At full size the oracle is out of reach, but the plain exact loop (no helper warps) is the code the small
-    parity tests pin against it.  With 24 replicates on 148 SMs every replicate runs with lookahead helpers and,
+    """The plain exact loop (no helper warps) against the loop with helpers.  With 24 replicates on 148 SMs every replicate runs with lookahead helpers and,
     once it has 64 clones, on the decoupled clock: the event logs (times bit for bit, patched into the records by
     the clock helper) and the summaries must equal those of the plain loop."""
     from jspace_b200 import _lib as L
@@ -116,12 +116,13 @@ def test_c3_3d_tree_excision_full(jsb):
 
 
 def test_c4_100k_node_geometric_graph_full(jsb):
-    from graphs import random_geometric_csr
-    rowptr, colidx = random_geometric_csr(100000, seed=4321)
+    from graphs import random_geometric_csr, geometric_centre
+    rowptr, colidx, pts = random_geometric_csr(100000, seed=4321, return_points=True)
     g = jsb.Graph.csr(rowptr, colidx)
     assert g.nv > 90000
-    # BFS-eccentricity proxy for the closeness centre (exact closeness is O(V*E) on the host)
-    centre = int(np.argmax(np.diff(rowptr))) + 1
+    # stand-in for the max-closeness vertex of src/J_Space.jl:83-85: the vertex nearest to the
+    # middle of the unit square; jsb_graph_seed_candidates computes the exact arg-max when none is supplied
+    centre = geometric_centre(pts)
     g.set_seed_candidates([centre])
     s = check_replicates(jsb, g, jsb.Point(**DEFAULT), 8, 1234, seeds_of=lambda i: [(centre, 1)])
     assert s["n_iterations"].max() > 1e5
