@@ -668,7 +668,9 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     }
     const uint64_t slots = (uint64_t)grid * wpb;
 
-    uint32_t arena_cap = (uint32_t)std::min<uint64_t>(4ull * g->nv + 2ull * kMinListCap * kTab, 0xFFFFFF00ull);
+    // sum of the block capacities after a compaction < 4*n_alive + kMinListCap*S, plus < kSeg entries of
+    // alignment in front of every block of 2*kSeg entries and more (those hold > kSeg/2 elements each)
+    uint32_t arena_cap = (uint32_t)std::min<uint64_t>(6ull * g->nv + 2ull * kMinListCap * kTab, 0xFFFFFF00ull);
     if (const char* dbg = std::getenv("JSB_DEBUG_ARENA_ENTRIES")) {  // test hook: force compactions
       uint64_t v = std::strtoull(dbg, nullptr, 10);
       arena_cap = (uint32_t)std::max<uint64_t>(v, 4096);  // too small -> JSB_ST_INTERNAL, never UB

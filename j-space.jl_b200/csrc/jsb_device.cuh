@@ -55,7 +55,7 @@ struct DevPoint {
 
 // Workspace layout per slot (all offsets 16-byte aligned); computed identically on host and device.
 struct WsLayout {
-  uint64_t clone, cellid, A, a_head, arena, inds, samp, c_cnt, c_cap, c_alpha, c_parent, c_label, g_w, g_c, ftree,
+  uint64_t clone, cellid, A, a_head, l_head, lseg, arena, inds, samp, c_cnt, c_cap, c_alpha, c_parent, c_label, g_w, g_c, ftree,
       total;
 };
 struct RunArgs {
@@ -116,6 +116,8 @@ __host__ __device__ inline WsLayout ws_layout(uint32_t nv, uint32_t arena_cap, u
   L.cellid = o;   o = jsb_align16(o + 4ull * nv);
   L.A = o;        o = jsb_align16(o + (uint64_t)site_bytes * ((uint64_t)nv + 1 + 512));  // tiered vector: whole segments of 256
   L.a_head = o;   o = jsb_align16(o + 2ull * (nv / 256 + 4));
+  L.l_head = o;   o = jsb_align16(o + 2ull * (arena_cap / 256 + 8));  // segment heads of the tiered ca_subpop blocks
+  L.lseg = o;     o = jsb_align16(o + (uint64_t)site_bytes * nv);  // per vertex: segment of its clone's list (hint)
   L.arena = o;    o = jsb_align16(o + (uint64_t)site_bytes * arena_cap + 32);
   L.inds = o;     o = jsb_align16(o + 4ull * nv);
   L.samp = o;     o = jsb_align16(o + 4ull * nv);

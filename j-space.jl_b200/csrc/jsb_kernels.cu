@@ -41,6 +41,7 @@ namespace jsb {
 
 #define FULL 0xffffffffu
 constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint32_t kSeg = 256;  // tiered-vector segment length (cs_alive and every long ca_subpop list)
 
 // Optional phase profiler (build with -DJSB_PROFILE; debug library only): per-replicate cycle
 // totals per phase, printed by lane 0 for the first replicates.
@@ -290,6 +291,8 @@ struct Ctx {
   uint32_t* cellid;
   T *Alist, *arena;
   uint16_t* a_head;         // tiered-vector segment heads of cs_alive
+  uint16_t* l_head;         // tiered-vector segment heads of the ca_subpop blocks, indexed by arena offset / kSeg
+  T* lseg;                  // per vertex: the segment of its clone's list that holds it (position hint, see list_remove_value)
   uint32_t *inds, *samp;
   T *c_off8, *c_len;        // per-warp shared slices [kTab]: arena offset / 8 and length of every clone's list,
                             // stored in the site type (u16 lattices: 4 KB instead of 8 KB per warp)
@@ -531,91 +534,6 @@ __device__ __forceinline__ uint32_t gc_cap(uint32_t len) {  // power of two >= m
   return c;
 }
 
-// Arena compaction, in place, order inside every list untouched.  Pass 1 squeezes the blocks
-// down in ascending-offset order (cap = len rounded to 16 bytes); pass 2 spreads them out again
-// from the last block to the first so that block i gets cap = max(min, 2*len).  Visited blocks
-// are tagged in the top bit of cap.  O(S^2/32) bookkeeping — only runs when clone turnover has
-// fragmented the arena.
-template <typename T>
-__device__ __noinline__ void arena_gc(Ctx<T>& X, Rep& r) {
-  const int lane = X.lane;
-  uint32_t top = 0;
-  for (uint32_t step = 0; step < r.S; ++step) {
-    uint32_t best = kNone, besti = kNone;
-    for (uint32_t i = lane; i < r.S; i += 32) {
-      uint32_t o = X.off(i);
-      if (!(X.c_cap[i] & 0x80000000u) && o < best) { best = o; besti = i; }
-    }
-    for (int d = 16; d > 0; d >>= 1) {
-      uint32_t ob = __shfl_xor_sync(FULL, best, d), oi = __shfl_xor_sync(FULL, besti, d);
-      if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
-    }
-    const uint32_t i = besti, l = X.c_len[i], src = best;
-    if (top != src) {
-      for (uint32_t b = 0; b < l; b += 32) {  // dst < src: ascending chunks are safe
-        uint32_t k = b + lane;
-        T v = 0;
-        if (k < l) v = X.arena[src + k];
-        __syncwarp();
-        if (k < l) X.arena[top + k] = v;
-        __syncwarp();
-      }
-    }
-    if (lane == 0) {
-      X.set_off(i, top);
-      X.c_cap[i] = round_cap(l) | 0x80000000u;
-    }
-    __syncwarp();
-    top += round_cap(l);
-  }
-  uint32_t total = 0;
-  for (uint32_t i = lane; i < r.S; i += 32) total += gc_cap(X.c_len[i]);
-  for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
-  if (total > X.A->arena_cap) {  // cannot happen when arena_cap >= 4*nv + kMinListCap*kTab
-    for (uint32_t i = lane; i < r.S; i += 32) X.c_cap[i] &= 0x7FFFFFFFu;
-    __syncwarp();
-    r.arena_top = top;
-    r.status = JSB_ST_INTERNAL;
-    return;
-  }
-  for (uint32_t step = 0; step < r.S; ++step) {
-    // still-tagged block with the largest (squeezed offset, index)
-    uint32_t best = 0, besti = kNone;
-    for (uint32_t i = lane; i < r.S; i += 32) {
-      uint32_t o = X.off(i);
-      if ((X.c_cap[i] & 0x80000000u) && (besti == kNone || o > best || (o == best && i > besti))) {
-        best = o; besti = i;
-      }
-    }
-    for (int d = 16; d > 0; d >>= 1) {
-      uint32_t ob = __shfl_xor_sync(FULL, best, d), oi = __shfl_xor_sync(FULL, besti, d);
-      if (oi != kNone && (besti == kNone || ob > best || (ob == best && oi > besti))) { best = ob; besti = oi; }
-    }
-    const uint32_t i = besti, l = X.c_len[i], src = best;
-    // new offset = total new capacity of the blocks not visited yet (all lie below src)
-    uint32_t noff = 0;
-    for (uint32_t q = lane; q < r.S; q += 32)
-      if (q != i && (X.c_cap[q] & 0x80000000u)) noff += gc_cap(X.c_len[q]);
-    for (int d = 16; d > 0; d >>= 1) noff += __shfl_xor_sync(FULL, noff, d);
-    if (noff != src && l > 0) {
-      for (uint32_t cb = (l + 31) / 32; cb-- > 0;) {  // dst > src: descending chunks are safe
-        uint32_t k = cb * 32 + lane;
-        T v = 0;
-        if (k < l) v = X.arena[src + k];
-        __syncwarp();
-        if (k < l) X.arena[noff + k] = v;
-        __syncwarp();
-      }
-    }
-    if (lane == 0) {
-      X.set_off(i, noff);
-      X.c_cap[i] = gc_cap(l);
-    }
-    __syncwarp();
-  }
-  r.arena_top = total;
-}
-
 // ---------------------------------------------------------------------------------------------
 // cs_alive as a tiered vector (Goodrich & Kloss): fixed segments of kSeg elements, each a circular
 // buffer with its own head; every segment but the last is full.  Element p lives in segment
@@ -624,8 +542,6 @@ __device__ __noinline__ void arena_gc(Ctx<T>& X, Rep& r) {
 // per following segment (its front becomes the previous segment's back) instead of shifting the
 // whole tail: ~n/2 elements (40 KB at n = 20 000) -> a few hundred bytes.
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t kSeg = 256;
-
 template <typename T>
 __device__ __forceinline__ uint32_t a_slot(const Ctx<T>& X, uint32_t p) {
   const uint32_t s = p / kSeg;
@@ -642,9 +558,10 @@ __device__ __forceinline__ void a_append(const Ctx<T>& X, uint32_t n, uint32_t s
   X.Alist[s * kSeg + ((X.a_head[s] + (n & (kSeg - 1u))) & (kSeg - 1u))] = (T)site;
 }
 
-// remove logical element p of n, keep order (whole warp)
+// remove logical element p of n, keep order (whole warp).  `hint` (may be null): per-vertex segment numbers,
+// kept up to date for the one element per later segment that changes segment.
 template <typename T>
-__device__ __noinline__ void a_remove(T* A, uint16_t* head, uint32_t n, uint32_t p, int lane) {
+__device__ __noinline__ void a_remove(T* A, uint16_t* head, uint32_t n, uint32_t p, int lane, T* hint) {
   const uint32_t s = p / kSeg, i = p & (kSeg - 1u);
   const uint32_t ls = (n - 1) / kSeg;                       // last segment
   const uint32_t cnt = (s == ls) ? ((n - 1) & (kSeg - 1u)) + 1u : kSeg;
@@ -680,10 +597,201 @@ __device__ __noinline__ void a_remove(T* A, uint16_t* head, uint32_t n, uint32_t
       const uint32_t slot = (t - 1 == s) ? ((hs + kSeg - 1u) & (kSeg - 1u)) : hp;
       A[(t - 1) * kSeg + slot] = v;
       head[t] = (uint16_t)((ht + 1u) & (kSeg - 1u));
+      if (hint) hint[v] = (T)(t - 1u);
     }
     prev_head_carry = last_ht;
     __syncwarp();
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The ca_subpop lists, tiered as well.  A list of at most kSeg elements is a flat array (any 16-byte
+// aligned place of the arena).  A longer one lives in a block of capacity >= 2*kSeg that starts on a
+// multiple of kSeg entries of the arena, and is a tiered vector whose segment heads sit in
+// l_head[arena offset / kSeg + segment]: `ca_subpop[i][x]` (:763) stays O(1) — one extra load of the
+// head — and filter!(e -> e != v, ca_subpop[i]) (:739,755; :411) moves at most kSeg elements plus one
+// per following segment instead of shifting the tail of an 80 KB list.  Invariant: whenever a list has
+// len <= kSeg its elements are stored flat from the block start (a list that shrinks to kSeg elements
+// is rotated back once), so small lists never look at a head.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ uint32_t l_get(const Ctx<T>& X, uint32_t off, uint32_t len, uint32_t x) {
+  if (len <= kSeg) return (uint32_t)X.arena[off + x];
+  const uint32_t s = x / kSeg;
+  const uint32_t h = X.l_head[off / kSeg + s];
+  return (uint32_t)X.arena[off + s * kSeg + ((h + (x & (kSeg - 1u))) & (kSeg - 1u))];
+}
+
+// logical position of `value` in a tiered list of len > kSeg elements (unique), kNone when absent.
+// Scans the raw storage of the segments in use; in the last (partial) segment a slot only counts when
+// it is one of the cnt live ones (a stale copy of the same vertex may sit in a dead slot).
+template <typename T>
+__device__ __noinline__ uint32_t tlist_find(const T* list, const uint16_t* head, uint32_t len, uint32_t value, int lane) {
+  constexpr uint32_t EPV = Vec<T>::EPV;
+  constexpr int U = 4;
+  const uint4* lv = reinterpret_cast<const uint4*>(list);
+  const uint32_t ls = (len - 1u) / kSeg;                      // last segment
+  const uint32_t cnt_last = ((len - 1u) & (kSeg - 1u)) + 1u;  // live elements in it
+  const uint32_t ngroups = (ls + 1u) * (kSeg / EPV);
+  for (uint32_t gb = 0; gb < ngroups; gb += 32 * U) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t g = gb + u * 32 + lane;
+      v[u] = make_uint4(kNone, kNone, kNone, kNone);
+      if (g < ngroups) v[u] = lv[g];
+    }
+    uint32_t hit = kNone;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      uint32_t g = gb + u * 32 + lane;
+      uint32_t m = g < ngroups ? Vec<T>::match(v[u], value) : 0u;
+      while (m) {
+        const uint32_t e = g * EPV + (uint32_t)__ffs(m) - 1u;  // raw element index
+        m &= m - 1u;
+        const uint32_t sg = e / kSeg;
+        const uint32_t j = (e - (uint32_t)head[sg]) & (kSeg - 1u);  // logical offset inside the segment
+        if (sg < ls || j < cnt_last) hit = sg * kSeg + j;
+      }
+    }
+    uint32_t bal = __ballot_sync(FULL, hit != kNone);
+    if (bal) return __shfl_sync(FULL, hit, __ffs(bal) - 1);
+  }
+  return kNone;
+}
+
+// the same inside ONE segment (raw storage `seg`, head h, cnt live elements): logical offset or kNone
+template <typename T>
+__device__ __noinline__ uint32_t tseg_find(const T* seg, uint32_t h, uint32_t cnt, uint32_t value, int lane) {
+  constexpr uint32_t EPV = Vec<T>::EPV;
+  constexpr uint32_t NG = kSeg / EPV;  // 16-byte groups per segment: 32 (u16) or 64 (u32)
+  const uint4* lv = reinterpret_cast<const uint4*>(seg);
+  uint32_t hit = kNone;
+#pragma unroll
+  for (uint32_t u = 0; u < NG / 32u; ++u) {
+    const uint32_t g = u * 32u + (uint32_t)lane;
+    uint32_t m = Vec<T>::match(lv[g], value);
+    while (m) {
+      const uint32_t e = g * EPV + (uint32_t)__ffs(m) - 1u;
+      m &= m - 1u;
+      const uint32_t j = (e - h) & (kSeg - 1u);
+      if (j < cnt) hit = j;
+    }
+  }
+  const uint32_t bal = __ballot_sync(FULL, hit != kNone);
+  return bal ? __shfl_sync(FULL, hit, __ffs(bal) - 1) : kNone;
+}
+
+// rotate the first segment of a block so that its head is 0 (the list just shrank to kSeg elements)
+template <typename T>
+__device__ __noinline__ void seg_normalise(T* seg, uint16_t* head, int lane) {
+  const uint32_t h = head[0];
+  __syncwarp();
+  if (h != 0) {
+    T v[kSeg / 32];
+#pragma unroll
+    for (uint32_t k = 0; k < kSeg / 32; ++k) v[k] = seg[(h + (uint32_t)lane + 32u * k) & (kSeg - 1u)];
+    __syncwarp();
+#pragma unroll
+    for (uint32_t k = 0; k < kSeg / 32; ++k) seg[(uint32_t)lane + 32u * k] = v[k];
+    if (lane == 0) head[0] = 0;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t align_seg(uint32_t o) { return (o + (kSeg - 1u)) & ~(kSeg - 1u); }
+
+// Arena compaction, in place, order inside every list untouched.  Pass 1 squeezes the blocks down in
+// ascending-offset order, each stored flat (cap = len rounded to 16 bytes; a tiered list goes through
+// the scratch array, its segments being rotations); the final offsets follow from one sequential walk
+// in that order (block i gets cap = max(min, 2*len) rounded up to a power of two, blocks of 2*kSeg and
+// more start on a multiple of kSeg); pass 2 spreads the blocks out again from the last to the first.
+// Afterwards every list is flat from its block start, so every head is 0.  Visited blocks are tagged in
+// the top bit of cap.  O(S^2/32) bookkeeping — only runs when clone turnover has fragmented the arena.
+template <typename T>
+__device__ __noinline__ void arena_gc(Ctx<T>& X, Rep& r) {
+  const int lane = X.lane;
+  // scratch: the tables of the exact prob_cum fallback (2*(kTab+8) words each; invalidated below) hold the
+  // visiting order of pass 1 and the final offsets — the clone count is not bounded by the lattice size
+  uint32_t* order = reinterpret_cast<uint32_t*>(X.g_w);
+  uint32_t* fin = reinterpret_cast<uint32_t*>(X.g_c);
+  uint32_t* lin = X.inds;    // a tiered list passes through here (len <= nv)
+  r.exact_valid = false;
+  uint32_t top = 0;
+  for (uint32_t step = 0; step < r.S; ++step) {
+    uint32_t best = kNone, besti = kNone;
+    for (uint32_t i = lane; i < r.S; i += 32) {
+      uint32_t o = X.off(i);
+      if (!(X.c_cap[i] & 0x80000000u) && o < best) { best = o; besti = i; }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+      uint32_t ob = __shfl_xor_sync(FULL, best, d), oi = __shfl_xor_sync(FULL, besti, d);
+      if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    const uint32_t i = besti, l = X.c_len[i], src = best;
+    if (l > kSeg) {  // tiered -> flat through the scratch array
+      for (uint32_t k = lane; k < l; k += 32) lin[k] = l_get(X, src, l, k);
+      __syncwarp();
+      for (uint32_t k = lane; k < l; k += 32) X.arena[top + k] = (T)lin[k];
+      __syncwarp();
+    } else if (top != src) {
+      for (uint32_t b = 0; b < l; b += 32) {  // dst < src: ascending chunks are safe
+        uint32_t k = b + lane;
+        T v = 0;
+        if (k < l) v = X.arena[src + k];
+        __syncwarp();
+        if (k < l) X.arena[top + k] = v;
+        __syncwarp();
+      }
+    }
+    if (lane == 0) {
+      X.set_off(i, top);
+      X.c_cap[i] = round_cap(l) | 0x80000000u;
+      order[step] = i;
+    }
+    __syncwarp();
+    top += round_cap(l);
+  }
+  // final offsets, in the same order
+  uint32_t total = 0;
+  if (lane == 0) {
+    for (uint32_t k = 0; k < r.S; ++k) {
+      const uint32_t cap = gc_cap(X.c_len[order[k]]);
+      if (cap >= 2u * kSeg) total = align_seg(total);
+      fin[k] = total;
+      total += cap;
+    }
+  }
+  total = __shfl_sync(FULL, total, 0);
+  __syncwarp();
+  if (total > X.A->arena_cap) {  // cannot happen when arena_cap >= 6*nv + kMinListCap*kTab
+    for (uint32_t i = lane; i < r.S; i += 32) X.c_cap[i] &= 0x7FFFFFFFu;
+    __syncwarp();
+    r.arena_top = top;
+    r.status = JSB_ST_INTERNAL;
+    return;
+  }
+  for (uint32_t k = r.S; k-- > 0;) {
+    const uint32_t i = order[k], l = X.c_len[i], src = X.off(i), noff = fin[k];
+    if (noff != src && l > 0) {
+      for (uint32_t cb = (l + 31) / 32; cb-- > 0;) {  // dst > src: descending chunks are safe
+        uint32_t q = cb * 32 + lane;
+        T v = 0;
+        if (q < l) v = X.arena[src + q];
+        __syncwarp();
+        if (q < l) X.arena[noff + q] = v;
+        __syncwarp();
+      }
+    }
+    if (lane == 0) {
+      X.set_off(i, noff);
+      X.c_cap[i] = gc_cap(l);
+    }
+    __syncwarp();
+  }
+  for (uint32_t q = lane; q < X.A->arena_cap / kSeg + 2u; q += 32) X.l_head[q] = 0;
+  __syncwarp();
+  r.arena_top = total;
 }
 
 // slow path of list_append: list c is full
@@ -691,19 +799,28 @@ template <typename T>
 __device__ __noinline__ bool list_grow(Ctx<T>& X, Rep& r, uint32_t c) {
   uint32_t len = X.c_len[c], cap = X.c_cap[c];
   uint32_t ncap = cap * 2;
-  if (r.arena_top + ncap > X.A->arena_cap) {
+  uint32_t dst = ncap >= 2u * kSeg ? align_seg(r.arena_top) : r.arena_top;
+  if (dst + ncap > X.A->arena_cap) {
     arena_gc(X, r);
     if (r.status == JSB_ST_INTERNAL) return false;
     len = X.c_len[c];
     cap = X.c_cap[c];
     if (len < cap) return true;
     ncap = cap * 2;
-    if (r.arena_top + ncap > X.A->arena_cap) { r.status = JSB_ST_INTERNAL; return false; }
+    dst = ncap >= 2u * kSeg ? align_seg(r.arena_top) : r.arena_top;
+    if (dst + ncap > X.A->arena_cap) { r.status = JSB_ST_INTERNAL; return false; }
   }
-  const uint32_t src = X.off(c), dst = r.arena_top;
+  // the list is full (len == cap): a tiered block is copied segment for segment with its heads, a flat one
+  // as it is (and, when the new block is a tiered one, becomes its first segment with head 0)
+  const uint32_t src = X.off(c);
   for (uint32_t b = 0; b < len; b += 32) {
     uint32_t k = b + X.lane;
     if (k < len) X.arena[dst + k] = X.arena[src + k];
+  }
+  if (ncap >= 2u * kSeg) {
+    const uint32_t nseg_old = cap >= 2u * kSeg ? cap / kSeg : 0u;
+    for (uint32_t q = X.lane; q < ncap / kSeg; q += 32)
+      X.l_head[dst / kSeg + q] = q < nseg_old ? X.l_head[src / kSeg + q] : (uint16_t)0;
   }
   __syncwarp();
   if (X.lane == 0) {
@@ -711,7 +828,7 @@ __device__ __noinline__ bool list_grow(Ctx<T>& X, Rep& r, uint32_t c) {
     X.c_cap[c] = ncap;
   }
   __syncwarp();
-  r.arena_top += ncap;
+  r.arena_top = dst + ncap;
   return true;
 }
 
@@ -729,24 +846,57 @@ __device__ __forceinline__ bool list_append(Ctx<T>& X, Rep& r, uint32_t c, uint3
     }
   }
   if (X.lane == 0) {
-    uint32_t len = X.c_len[c];
-    X.arena[X.off(c) + len] = (T)site;
+    const uint32_t len = X.c_len[c], off = X.off(c);
+    if (len < kSeg) {
+      X.arena[off + len] = (T)site;
+    } else {  // the block holds >= 2*kSeg entries and starts on a multiple of kSeg
+      const uint32_t sg = len / kSeg, hi = off / kSeg + sg;
+      if ((len & (kSeg - 1u)) == 0) X.l_head[hi] = 0;
+      X.arena[off + sg * kSeg + ((X.l_head[hi] + (len & (kSeg - 1u))) & (kSeg - 1u))] = (T)site;
+    }
+    X.lseg[site] = (T)(len / kSeg);
     X.c_len[c] = (T)(len + 1);
   }
   __syncwarp();
   return true;
 }
 
-// filter!(e -> e != site, ca_subpop[c])
+// filter!(e -> e != site, ca_subpop[c]).  The reference scans the list for the vertex; here lseg[site]
+// names the segment that holds it (every operation that moves an element to another segment keeps it up to
+// date: appends, the one-per-segment hand-over of a tiered delete, the excision rebuild), so only kSeg
+// entries are searched.  A wrong hint would still be found by the full scan, and is reported as an
+// internal error so that the tests see it.
 template <typename T>
-__device__ __forceinline__ void list_remove_value(Ctx<T>& X, uint32_t c, uint32_t site) {
-  uint32_t len = X.c_len[c];
-  T* list = X.arena + X.off(c);
-  uint32_t idx = list_find<T>(list, len, site, X.lane);
-  if (idx != kNone) {
-    list_remove_at<T>(list, len, idx, X.lane);
-    if (X.lane == 0) X.c_len[c] = (T)(len - 1);
-    __syncwarp();
+__device__ __forceinline__ void list_remove_value(Ctx<T>& X, Rep& r, uint32_t c, uint32_t site) {
+  const uint32_t len = X.c_len[c], off = X.off(c);
+  T* list = X.arena + off;
+  if (len <= kSeg) {
+    uint32_t idx = list_find<T>(list, len, site, X.lane);
+    if (idx != kNone) {
+      list_remove_at<T>(list, len, idx, X.lane);
+      if (X.lane == 0) X.c_len[c] = (T)(len - 1);
+      __syncwarp();
+    }
+  } else {
+    uint16_t* head = X.l_head + off / kSeg;
+    const uint32_t ls = (len - 1u) / kSeg;
+    uint32_t sg = (uint32_t)X.lseg[site];
+    uint32_t p = kNone;
+    if (sg <= ls) {
+      const uint32_t cnt = sg == ls ? ((len - 1u) & (kSeg - 1u)) + 1u : kSeg;
+      const uint32_t j = tseg_find<T>(list + sg * kSeg, head[sg], cnt, site, X.lane);
+      if (j != kNone) p = sg * kSeg + j;
+    }
+    if (p == kNone) {
+      p = tlist_find<T>(list, head, len, site, X.lane);
+      if (p != kNone) r.status = JSB_ST_INTERNAL;  // stale hint
+    }
+    if (p != kNone) {
+      a_remove<T>(list, head, len, p, X.lane, X.lseg);
+      if (X.lane == 0) X.c_len[c] = (T)(len - 1);
+      __syncwarp();
+      if (len - 1u == kSeg) seg_normalise<T>(list, head, X.lane);
+    }
   }
 }
 
@@ -767,6 +917,7 @@ __device__ __noinline__ bool new_clone(Ctx<T>& X, Rep& r, uint32_t parent1, uint
     X.c_parent[c] = (uint16_t)parent1;
     X.c_label[c] = (uint16_t)label;
     X.arena[r.arena_top] = (T)first_site;
+    X.lseg[first_site] = 0;
   }
   __syncwarp();
   r.arena_top += kMinListCap;
@@ -939,7 +1090,6 @@ __device__ __forceinline__ void eval_member(const Ctx<T>& X, const Rep& r, uint6
   const bool is_birth = cls < S;
   const uint32_t ci = is_birth ? cls : 0u;
   const uint32_t off = lds_tab<T>(X.sOff, ci) << 3, cl = lds_tab<T>(X.sLen, ci);
-  const T* list = X.arena + off;
   const uint32_t llen = is_birth ? cl : r.n;
   // cls >= S+2: findfirst -> nothing in the reference; llen == 0: rand(1:0) throws.  Contract:
   // both are null iterations.
@@ -948,7 +1098,7 @@ __device__ __forceinline__ void eval_member(const Ctx<T>& X, const Rep& r, uint6
   cell = 0;
   if (valid) {
     x = bounded(X.key, w_cell, llen, q, DS_CELL_NBR, 0, 0);  // :727 / :746 / :762
-    cell = is_birth ? (uint32_t)list[x] : a_get(X, x);
+    cell = is_birth ? l_get(X, off, cl, x) : a_get(X, x);
   }
 }
 
@@ -1080,8 +1230,8 @@ __device__ __forceinline__ void apply_migration(Ctx<T>& X, Rep& r, const Eval& e
   __syncwarp();
   log_row(X, r, JSB_EV_MIGRATION, JSB_EVF_GROUP_START, r.t, cid, 0, e.pos, e.cell + 1, cl, 0);
   list_append(X, r, cl - 1, e.pos);                   // push!(ca_subpop[idx], pos)
-  a_remove<T>(X.Alist, X.a_head, r.n + 1, e.x, X.lane);  // filter!(e -> e != cell, cs_alive)
-  list_remove_value(X, cl - 1, e.cell);               // filter!(e -> e != cell, ca_subpop[idx])
+  a_remove<T>(X.Alist, X.a_head, r.n + 1, e.x, X.lane, nullptr);  // filter!(e -> e != cell, cs_alive)
+  list_remove_value(X, r, cl - 1, e.cell);               // filter!(e -> e != cell, ca_subpop[idx])
   r.n_eff++;
   r.n_migr++;
 }
@@ -1094,8 +1244,8 @@ __device__ __forceinline__ uint32_t apply_death(Ctx<T>& X, Rep& r, const Eval& e
   log_row(X, r, JSB_EV_DEATH, JSB_EVF_GROUP_START, r.t, cid, 0, e.cell, 0, cl, 0);
   if (X.lane == 0) { X.clone[e.cell] = 0; occ_clear(X.occ, e.cell); }
   __syncwarp();
-  a_remove<T>(X.Alist, X.a_head, r.n, e.x, X.lane);
-  list_remove_value(X, cl - 1, e.cell);
+  a_remove<T>(X.Alist, X.a_head, r.n, e.x, X.lane, nullptr);
+  list_remove_value(X, r, cl - 1, e.cell);
   r.n -= 1;
   r.n_eff++;
   r.n_deaths++;
@@ -1183,7 +1333,7 @@ __device__ __forceinline__ bool apply_birth(Ctx<T>& X, Rep& r, const Eval& e) {
   if (e.occ != 0) {  // :335-338 displacement (voter rules); e.occ was read by the caller
     uint32_t pid = X.track_ids ? X.cellid[e.pos] : 0u;
     __syncwarp();
-    list_remove_value(X, e.occ - 1, e.pos);
+    list_remove_value(X, r, e.occ - 1, e.pos);
     mark_dirty(r, e.occ - 1);
     log_row(X, r, JSB_EV_DEATH, JSB_EVF_DISPLACED | first_flag, r.t, pid, 0, e.pos, 0, e.occ, 0);
     first_flag = 0;
@@ -1238,7 +1388,7 @@ __device__ __forceinline__ bool apply_birth(Ctx<T>& X, Rep& r, const Eval& e) {
       }
       __syncwarp();
       if (!list_append(X, r, sp - 1, e.pos)) return false;
-      list_remove_value(X, sp - 1, e.cell);
+      list_remove_value(X, r, sp - 1, e.cell);
       { Ctx<T> xc = X; Rep rc = r; const bool ok = new_clone(xc, rc, sp, label, nalpha, e.cell); r = rc; if (!ok) return false; }
     }
   }
@@ -1377,17 +1527,34 @@ __device__ __noinline__ void apply_excision(Ctx<T>& X, Rep& r, double tb, double
     __syncwarp();
   }
   for (uint32_t c = 0; c < r.S; ++c) {
-    uint32_t len = X.c_len[c];
-    T* list = X.arena + X.off(c);
+    const uint32_t len = X.c_len[c], off = X.off(c);
+    T* list = X.arena + off;
     uint32_t wpos = 0;
-    for (uint32_t base = 0; base < len; base += 32) {
-      uint32_t i = base + lane;
-      T v = 0;
-      bool keep = false;
-      if (i < len) { v = list[i]; keep = X.clone[v] != 0; }
-      uint32_t m = __ballot_sync(FULL, keep);
-      if (keep) list[wpos + __popc(m & ((1u << lane) - 1u))] = v;
-      wpos += __popc(m);
+    if (len <= kSeg) {  // flat: in place (a kept element never moves up)
+      for (uint32_t base = 0; base < len; base += 32) {
+        uint32_t i = base + lane;
+        T v = 0;
+        bool keep = false;
+        if (i < len) { v = list[i]; keep = X.clone[v] != 0; }
+        uint32_t m = __ballot_sync(FULL, keep);
+        __syncwarp();
+        if (keep) list[wpos + __popc(m & ((1u << lane) - 1u))] = v;
+        wpos += __popc(m);
+        __syncwarp();
+      }
+    } else {            // tiered: through the scratch array, rebuilt flat with every head 0
+      for (uint32_t base = 0; base < len; base += 32) {
+        uint32_t i = base + lane;
+        uint32_t v = 0;
+        bool keep = false;
+        if (i < len) { v = l_get(X, off, len, i); keep = X.clone[v] != 0; }
+        uint32_t m = __ballot_sync(FULL, keep);
+        if (keep) inds[wpos + __popc(m & ((1u << lane) - 1u))] = v;
+        wpos += __popc(m);
+      }
+      __syncwarp();
+      for (uint32_t i = lane; i < wpos; i += 32) { list[i] = (T)inds[i]; X.lseg[inds[i]] = (T)(i / kSeg); }
+      for (uint32_t sg = lane; sg <= (len - 1u) / kSeg; sg += 32) X.l_head[off / kSeg + sg] = 0;
       __syncwarp();
     }
     if (lane == 0) X.c_len[c] = (T)(wpos);
@@ -1412,6 +1579,7 @@ __device__ __noinline__ void seed_replicate(Ctx<T>& X, Rep& r) {
     for (uint32_t i = lane; i < X.A->occ_words; i += 32) X.occ[i] = 0;
   for (uint32_t i = lane; i < (uint32_t)kSmemTable; i += 32) X.B[i] = __longlong_as_double(0x7ff0000000000000ll);  // +inf pad
   for (uint32_t sg = lane; sg * kSeg <= (uint32_t)(P.n_start > 1 ? P.n_start : 1); sg += 32) X.a_head[sg] = 0;
+  for (uint32_t q = lane; q < X.A->arena_cap / kSeg + 2u; q += 32) X.l_head[q] = 0;
   __syncwarp();
   uint32_t n0 = 0;
   if (P.n_start == 1) {
@@ -1427,6 +1595,7 @@ __device__ __noinline__ void seed_replicate(Ctx<T>& X, Rep& r) {
         X.clone[v0] = 1;
         X.cellid[v0] = 1;
         X.Alist[0] = (T)v0;
+        X.lseg[v0] = 0;
         occ_set(X.occ, v0);
       }
       n0 = 1;
@@ -1450,7 +1619,7 @@ __device__ __noinline__ void seed_replicate(Ctx<T>& X, Rep& r) {
         X.cellid[pos] = (uint32_t)i + 1;
         occ_set(X.occ, pos);
       }
-      for (uint32_t q = 0; q < cnt; ++q) X.Alist[q] = (T)X.samp[q];
+      for (uint32_t q = 0; q < cnt; ++q) { X.Alist[q] = (T)X.samp[q]; X.lseg[X.samp[q]] = (T)(q / kSeg); }
     }
     n0 = (uint32_t)P.n_start;
   }
@@ -1536,9 +1705,8 @@ __device__ __noinline__ void write_outputs(Ctx<T>& X, Rep& r) {
     for (uint32_t i = lane; i < r.n; i += 32) la[i] = a_get(X, i) + 1;
     uint32_t wpos = 0;
     for (uint32_t c = 0; c < r.S; ++c) {
-      uint32_t len = X.c_len[c];
-      const T* list = X.arena + X.off(c);
-      for (uint32_t i = lane; i < len; i += 32) ll[wpos + i] = (uint32_t)list[i] + 1;
+      const uint32_t len = X.c_len[c], off = X.off(c);
+      for (uint32_t i = lane; i < len; i += 32) ll[wpos + i] = l_get(X, off, len, i) + 1;
       wpos += len;
     }
   }
@@ -2374,6 +2542,8 @@ __device__ __forceinline__ Ctx<T> make_ctx(const RunArgs& A, unsigned char* s_dy
   X.Alist = reinterpret_cast<T*>(base + L.A);
   X.arena = reinterpret_cast<T*>(base + L.arena);
   X.a_head = reinterpret_cast<uint16_t*>(base + L.a_head);
+  X.l_head = reinterpret_cast<uint16_t*>(base + L.l_head);
+  X.lseg = reinterpret_cast<T*>(base + L.lseg);
   X.inds = reinterpret_cast<uint32_t*>(base + L.inds);
   X.samp = reinterpret_cast<uint32_t*>(base + L.samp);
   X.c_cap = reinterpret_cast<uint32_t*>(base + L.c_cap);

@@ -172,6 +172,21 @@ def test_arena_compaction(jsb, oracle, monkeypatch):
     assert max(int(x["n_clones"]) for x in s) > 100 and all(int(x["status"]) == 0 for x in s)
 
 
+def test_arena_compaction_with_tiered_lists(jsb, oracle, monkeypatch):
+    # lists longer than one tiered-vector segment (256 entries) in an arena so small that it is compacted
+    # again and again: tiered -> flat squeeze, aligned re-spread, head resets, growth of tiered blocks,
+    # the shrink-to-one-segment rotation (voter turnover empties and refills clones)
+    monkeypatch.setenv("JSB_DEBUG_ARENA_ENTRIES", "16000")
+    p = dict(DEFAULT, rule="voter", Tf=90.0, rate_birth=0.5, mu_driver=0.003, rate_death=0.05, rate_migration=0.05)
+    s = compare_runs(jsb, oracle, ("lattice", 2, 64, 64), p, reps=4)
+    assert max(int(x["n_alive"]) for x in s) > 1000 and all(int(x["status"]) == 0 for x in s)
+    # and with excisions in the middle of it (tiered lists rebuilt flat through the scratch array)
+    p = dict(DEFAULT, Tf=70.0, rate_birth=0.6, rate_death=0.03, t_bottleneck=[30.0, 50.0], ratio_bottleneck=[0.6, 0.3],
+             quirk_flags=1)
+    s = compare_runs(jsb, oracle, ("lattice", 2, 64, 64), p, reps=4)
+    assert max(int(x["n_excised"]) for x in s) > 300 and all(int(x["status"]) == 0 for x in s)
+
+
 def test_clone_capacity_stop(jsb, oracle):
     # 1000 clones = every label of Set(1:1000) used: the reference throws at :371; both sides stop
     p = dict(DEFAULT, rule="voter", Tf=150.0, mu_driver=0.1, rate_death=0.05)
