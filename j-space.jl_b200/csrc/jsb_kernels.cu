@@ -560,47 +560,69 @@ __device__ __forceinline__ void a_append(const Ctx<T>& X, uint32_t n, uint32_t s
 
 // remove logical element p of n, keep order (whole warp).  `hint` (may be null): per-vertex segment numbers,
 // kept up to date for the one element per later segment that changes segment.
+// Latency is what matters here (one warp, dependent global-memory round trips): every load of the
+// in-segment shift and of the first 128 later segments is issued before the first store — head[s], then
+// {in-segment elements, later heads}, then the later segments' fronts: three round trips per delete.
 template <typename T>
 __device__ __noinline__ void a_remove(T* A, uint16_t* head, uint32_t n, uint32_t p, int lane, T* hint) {
+  constexpr uint32_t K = 4;          // later segments per lane and pass
+  constexpr uint32_t R = kSeg / 32;  // in-segment elements per lane
   const uint32_t s = p / kSeg, i = p & (kSeg - 1u);
-  const uint32_t ls = (n - 1) / kSeg;                       // last segment
+  const uint32_t ls = (n - 1) / kSeg;  // last segment
   const uint32_t cnt = (s == ls) ? ((n - 1) & (kSeg - 1u)) + 1u : kSeg;
   const uint32_t hs = head[s];
   T* seg = A + s * kSeg;
   // inside segment s: logical j <- j+1 for j in [i, cnt-1)
-  for (uint32_t base = i; base + 1 < cnt; base += 32) {
-    const uint32_t j = base + lane;
-    T v = 0;
-    const bool act = j + 1 < cnt;
-    if (act) v = seg[(hs + j + 1) & (kSeg - 1u)];
-    __syncwarp();
-    if (act) seg[(hs + j) & (kSeg - 1u)] = v;
-    __syncwarp();
+  T v[R];
+#pragma unroll
+  for (uint32_t k = 0; k < R; ++k) {
+    const uint32_t j = i + (uint32_t)lane + 32u * k;
+    v[k] = 0;
+    if (j + 1 < cnt) v[k] = seg[(hs + j + 1) & (kSeg - 1u)];
   }
-  // every later segment hands its front to the back of its predecessor and rotates by one
-  uint32_t prev_head_carry = hs;  // head of segment t-1 before this call, for the first lane
-  for (uint32_t base = s + 1; base <= ls; base += 32) {
-    const uint32_t t = base + lane;
-    const bool act = t <= ls;
-    uint32_t ht = 0, hp = 0;
-    T v = 0;
-    if (act) {
-      ht = head[t];
-      hp = (lane == 0) ? prev_head_carry : (uint32_t)head[t - 1];
-      v = A[t * kSeg + ht];
+  // every later segment t hands its front to the back of t-1 and rotates by one.  Back slot of t-1:
+  // segment s kept its head (slot head + kSeg - 1); a later one rotated, so its new back is its old front slot.
+  bool first_pass = true;
+  for (uint32_t base = s + 1; base <= ls || first_pass; base += 32u * K) {
+    uint32_t ht[K], hp[K];
+    T f[K];
+#pragma unroll
+    for (uint32_t k = 0; k < K; ++k) {
+      const uint32_t t = base + (uint32_t)lane + 32u * k;
+      ht[k] = hp[k] = 0;
+      if (t <= ls) {
+        ht[k] = head[t];
+        hp[k] = head[t - 1];
+        // the previous pass already advanced the head of its last segment
+        if (!first_pass && t == base) hp[k] = (hp[k] + kSeg - 1u) & (kSeg - 1u);
+      }
     }
-    const uint32_t last_ht = __shfl_sync(FULL, ht, 31);
-    __syncwarp();
-    if (act) {
-      // back slot of t-1: segment s kept its head (slot head+kSeg-1); later ones rotated, so their
-      // new back is their old front slot
-      const uint32_t slot = (t - 1 == s) ? ((hs + kSeg - 1u) & (kSeg - 1u)) : hp;
-      A[(t - 1) * kSeg + slot] = v;
-      head[t] = (uint16_t)((ht + 1u) & (kSeg - 1u));
-      if (hint) hint[v] = (T)(t - 1u);
+#pragma unroll
+    for (uint32_t k = 0; k < K; ++k) {
+      const uint32_t t = base + (uint32_t)lane + 32u * k;
+      f[k] = 0;
+      if (t <= ls) f[k] = A[t * kSeg + ht[k]];
     }
-    prev_head_carry = last_ht;
     __syncwarp();
+    if (first_pass) {
+#pragma unroll
+      for (uint32_t k = 0; k < R; ++k) {
+        const uint32_t j = i + (uint32_t)lane + 32u * k;
+        if (j + 1 < cnt) seg[(hs + j) & (kSeg - 1u)] = v[k];
+      }
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < K; ++k) {
+      const uint32_t t = base + (uint32_t)lane + 32u * k;
+      if (t <= ls) {
+        const uint32_t slot = (t - 1 == s) ? ((hs + kSeg - 1u) & (kSeg - 1u)) : hp[k];
+        A[(t - 1) * kSeg + slot] = f[k];
+        head[t] = (uint16_t)((ht[k] + 1u) & (kSeg - 1u));
+        if (hint) hint[f[k]] = (T)(t - 1u);
+      }
+    }
+    __syncwarp();
+    first_pass = false;
   }
 }
 

@@ -94,6 +94,8 @@ struct OrcParams {  // same field order as jsb_params
 enum { RULE_CONTACT = 0, RULE_VOTER = 1, RULE_HVOTER = 2, RULE_NONE = 3 };
 enum { QUIRK_EXCISION_INTENT = 1 };
 
+#include "julia_mt.hpp"
+
 // -------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11).  Checked against the Random123
 // known-answer vectors in tests/test_oracle_rng.py.
@@ -343,6 +345,10 @@ struct Sim {
   uint64_t iter = 0;
   uint32_t next_id = 1;
   OrcSummary sum{};
+  // Reference-stream mode (julia_mt.hpp): when set, every draw is taken from the reference's own
+  // MersenneTwister in the reference's call order instead of the counter-based draw contract.
+  jmt::MersenneTwister* mt = nullptr;
+  const jmt::IntSet* label_set = nullptr;  // slot layout of Set(1:1000), src/J_Space.jl:366
   // benchmark control (bench.py's time-boxed CPU arm): iterations done so far / stop request
   volatile uint64_t* progress = nullptr;
   volatile int* stop = nullptr;
@@ -369,6 +375,10 @@ struct Sim {
     df.push_back(e);
   }
   void push_series() { series_n.push_back((uint32_t)n_cs_alive); }
+  // rand(seed, 1:s) / rand(seed, v::Vector) index, 0-based
+  uint64_t draw_index(uint32_t site, uint32_t seq, int half, uint64_t s) {
+    return mt ? mt->rand_index(s) : rng.index(iter, site, seq, half, s);
+  }
 
   // initialize_graph, src/J_Space.jl:79-119 (generic) and :122-163 (lattice)
   void seed_cells(const std::vector<int64_t>& candidates) {
@@ -385,9 +395,8 @@ struct Sim {
         if ((double)v0 != v || v0 < 1 || v0 > G.nv) v0 = 0;  // `i == v₀` never true
       } else {
         // :83-86  v₀ = rand(seed, pos_value)
-        uint64_t j = candidates.size() > 1
-                         ? rng.index(0, DS_SEED_TIE, 0, 0, candidates.size())
-                         : 0;
+        uint64_t j = mt ? mt->rand_index(candidates.size())  // rand(seed, pos_value) always draws
+                        : (candidates.size() > 1 ? rng.index(0, DS_SEED_TIE, 0, 0, candidates.size()) : 0);
         v0 = candidates[j];
       }
       if (v0) seeded.push_back((int32_t)v0);
@@ -395,7 +404,17 @@ struct Sim {
       // :105-112 / :151-157  positions = Set(1:nv); pos = rand(seed, positions); delete!
       // contract: the j-th smallest remaining position, j uniform
       std::vector<int32_t> chosen_sorted;
-      for (int i = 0; i < n_cell; ++i) {
+      if (mt) {  // reference stream: id = uuid1(seed); pos = rand(seed, positions::Set); delete!(positions, pos)
+        jmt::IntSet positions = jmt::IntSet::range(G.nv, mt->var);
+        std::vector<char> gone((size_t)G.nv + 1, 0);
+        for (int i = 0; i < n_cell; ++i) {
+          mt->uuid1();
+          int64_t pos = mt->rand_set(positions, reinterpret_cast<const bool*>(gone.data()));
+          gone[pos] = 1;
+          seeded.push_back((int32_t)pos);
+        }
+      }
+      for (int i = 0; i < n_cell && !mt; ++i) {
         uint64_t remaining = (uint64_t)G.nv - (uint64_t)i;
         uint64_t j = rng.index(0, DS_SEED_POS, (uint32_t)i, 0, remaining);
         int64_t pos = (int64_t)j + 1;  // rank among remaining, 1-based
@@ -407,6 +426,7 @@ struct Sim {
       }
     }
     for (int32_t v : seeded) {
+      if (mt && n_cell == 1) mt->uuid1();
       id[v] = next_id++;  // id = uuid1(seed)
       subpop[v] = 1;      // :mutation => 1 ; :Subpop by :675-680
     }
@@ -448,6 +468,7 @@ struct Sim {
 
   // randn by the polar method on contract draws
   double randn() {
+    if (mt) return mt->randn();
     for (uint32_t attempt = 0;; ++attempt) {
       uint64_t a, b;
       rng.block(iter, 0, DS_NORMAL, attempt, a, b);
@@ -464,9 +485,16 @@ struct Sim {
   bool cell_birth(int32_t cell, int32_t pos, double time, int idx) {
     // The two uniforms of this birth (driver test and placement coin) are counter-keyed, so
     // they can be read before the displacement below without changing anything.
-    uint64_t wa, wb;
-    rng.block(iter, 0, DS_DRIVER_COIN, 0, wa, wb);
-    double r = u01_53(wa);  // :347 / :447
+    uint64_t wa = 0, wb = 0;
+    double r;
+    if (mt) {  // reference order: (displacement draws nothing) id, id2 = uuid1 x2 :340-341, then r :347
+      mt->uuid1();
+      mt->uuid1();
+      r = mt->rand_float();
+    } else {
+      rng.block(iter, 0, DS_DRIVER_COIN, 0, wa, wb);
+      r = u01_53(wa);  // :347 / :447
+    }
     int32_t sp = subpop[cell];
 
     int child_node = -1;  // method 2: eligible tree child
@@ -522,13 +550,17 @@ struct Sim {
     } else {
       // :366-371  possible_mut = Set(1:1000) minus used; new_drive = rand(seed, possible_mut)
       int n_free = 1000 - n_used;
-      uint64_t j = rng.index(iter, DS_LABEL, 0, 0, (uint64_t)n_free);  // rank among unused
       int lab = 0;
-      for (int m = 1; m <= 1000; ++m)
-        if (!used_label[m]) {
-          if (j == 0) { lab = m; break; }
-          --j;
-        }
+      if (mt) {
+        lab = (int)mt->rand_set(*label_set, used_label);  // rand(seed, possible_mut::Set{Int}) :371
+      } else {
+        uint64_t j = rng.index(iter, DS_LABEL, 0, 0, (uint64_t)n_free);  // rank among unused
+        for (int m = 1; m <= 1000; ++m)
+          if (!used_label[m]) {
+            if (j == 0) { lab = m; break; }
+            --j;
+          }
+      }
       used_label[lab] = true;
       ++n_used;
       new_label = (uint16_t)lab;
@@ -542,7 +574,7 @@ struct Sim {
     set_mut.push_back(c);  // :384 / :506
     int new_sp = (int)set_mut.size();
 
-    bool coin = u01_53(wb) < 0.5;  // :391 / :512
+    bool coin = (mt ? mt->rand_float() : u01_53(wb)) < 0.5;  // :391 / :512
     // :387-388 / :508-509 (rows are pushed before the coin; their content does not depend on it
     // except for the vertex we additionally record)
     log(EV_MUTATION, first_flag, time, nid2, parent, (uint32_t)(coin ? pos : cell), 0, (uint16_t)new_sp,
@@ -570,7 +602,7 @@ struct Sim {
     std::vector<int32_t> x((size_t)k);
     int64_t n = (int64_t)a.size();
     uint32_t q = 0;
-    auto draw = [&](uint64_t s) { return (int64_t)rng.index(iter, DS_EXCISION, q++, 0, s); };
+    auto draw = [&](uint64_t s) { return (int64_t)(mt ? mt->rand_index(s) : rng.index(iter, DS_EXCISION, q++, 0, s)); };
     if (k == 0) return x;
     if (k == 1) {
       x[0] = a[draw((uint64_t)n)];
@@ -623,9 +655,14 @@ struct Sim {
       double death = P.rate_death * (double)n_cs_alive;     // :696
       double M = P.rate_migration * (double)n_cs_alive;     // :697
       double lambda = birth + death + M;                    // :698
-      uint64_t wa, wb;
-      rng.block(iter, 0, DS_TIME_CLASS, 0, wa, wb);
-      double t_event = (-contract_log(u01_open(wa))) * (1.0 / lambda);  // :699 θ·randexp
+      uint64_t wa = 0, wb = 0;
+      double t_event;
+      if (mt) {
+        t_event = mt->randexp() * (1.0 / lambda);  // rand(seed, Exponential(1 / λ), 1)[1] :699
+      } else {
+        rng.block(iter, 0, DS_TIME_CLASS, 0, wa, wb);
+        t_event = (-contract_log(u01_open(wa))) * (1.0 / lambda);  // :699 θ·randexp
+      }
       double t_old = t_curr;                                // :700
       t_curr += t_event;                                    // :701
 
@@ -646,7 +683,7 @@ struct Sim {
       prob_cum.resize(S + 2);
       accumulate_pairwise(prob_vet, prob_cum);
 
-      double k = u01_53(wb);  // :721
+      double k = mt ? mt->rand_float() : u01_53(wb);  // :721
       int min = 0;            // findfirst(k .<= prob_cum) :722-723 (1-based; 0 = nothing)
       for (int i = 0; i < S + 2; ++i)
         if (k <= prob_cum[i]) { min = i + 1; break; }
@@ -655,11 +692,11 @@ struct Sim {
       if (min == 0) {
         // reference: `nothing` -> MethodError.  Contract: null iteration.
       } else if (min == S + 2) {  // Migration :725-742
-        int64_t x = (int64_t)rng.index(iter, DS_CELL_NBR, 0, 0, (uint64_t)n_cs_alive);
+        int64_t x = (int64_t)draw_index(DS_CELL_NBR, 0, 0, (uint64_t)n_cs_alive);
         int32_t cell = cs_alive[x];
         const auto& nb = G.nbr[cell];
         if (!nb.empty()) {
-          int32_t pos = nb[rng.index(iter, DS_CELL_NBR, 0, 1, nb.size())];
+          int32_t pos = nb[draw_index(DS_CELL_NBR, 0, 1, nb.size())];
           if (!in_alive(pos)) {
             int idx = subpop[cell];
             migration_cell(cell, pos, t_curr);
@@ -672,7 +709,7 @@ struct Sim {
           }
         }
       } else if (min == S + 1) {  // Death :744-759
-        int64_t x = (int64_t)rng.index(iter, DS_CELL_NBR, 0, 0, (uint64_t)n_cs_alive);
+        int64_t x = (int64_t)draw_index(DS_CELL_NBR, 0, 0, (uint64_t)n_cs_alive);
         int32_t cell = cs_alive[x];
         int idx = subpop[cell];
         cell_death(cell, t_curr, EVF_GROUP_START);
@@ -684,11 +721,11 @@ struct Sim {
       } else {  // Birth :761-810
         const auto& members = ca_subpop[min - 1];
         if (!members.empty()) {  // rand(seed, 1:0) would throw; contract: null iteration
-          int64_t x = (int64_t)rng.index(iter, DS_CELL_NBR, 0, 0, members.size());
+          int64_t x = (int64_t)draw_index(DS_CELL_NBR, 0, 0, members.size());
           int32_t cell = members[x];
           const auto& nb = G.nbr[cell];
           if (!nb.empty()) {
-            int32_t pos = nb[rng.index(iter, DS_CELL_NBR, 0, 1, nb.size())];
+            int32_t pos = nb[draw_index(DS_CELL_NBR, 0, 1, nb.size())];
             bool rule = true;  // :767-786
             if (P.rule == RULE_CONTACT) {
               if (in_alive(pos)) rule = false;
@@ -857,6 +894,39 @@ void* orc_run_ctl(void* g, const OrcParams* p, uint64_t seed, uint32_t stream, c
   s->seed_cells(cand);
   s->run();
   return s;
+}
+// One replicate on the REFERENCE's own random stream: MersenneTwister(mt_seed) restated in julia_mt.hpp, every
+// draw in the reference's call order (src/Start.jl:12-13 -> spatial_graph -> simulate_evolution).  `variant`
+// = {set_slots, sizehint_mode, hash_float, range_fast, set_ndl, int_fill_tail}; null = the defaults.
+void* orc_run_mt(void* g, const OrcParams* p, uint64_t mt_seed, const int32_t* variant, const int64_t* candidates,
+                 int64_t n_candidates) {
+  Graph* G = (Graph*)g;
+  jmt::Variant v;
+  if (variant) {
+    v.set_slots = variant[0]; v.sizehint_mode = variant[1]; v.hash_float = variant[2] != 0;
+    v.range_fast = variant[3] != 0; v.set_ndl = variant[4] != 0; v.int_fill_tail = variant[5];
+  }
+  jmt::MersenneTwister mt(mt_seed, v);
+  jmt::IntSet labels = jmt::IntSet::range(1000, v);
+  Sim* s = new Sim(*G, *p, 0, 0, false);
+  s->mt = &mt;
+  s->label_set = &labels;
+  std::vector<int64_t> cand;
+  if (candidates) cand.assign(candidates, candidates + n_candidates);
+  if (!G->is_lattice && p->n_start_cells == 1 && cand.empty()) cand = closeness_argmax(*G);
+  s->seed_cells(cand);
+  s->run();
+  s->mt = nullptr;
+  s->label_set = nullptr;
+  return s;
+}
+// the first n doubles rand(MersenneTwister(seed)) returns, and one randn / randexp after them (known-answer checks)
+void orc_mt_probe(uint64_t mt_seed, double* floats, int n, double* normal, double* expo) {
+  jmt::Variant v;
+  jmt::MersenneTwister a(mt_seed, v), b(mt_seed, v), c(mt_seed, v);
+  for (int i = 0; i < n; ++i) floats[i] = a.rand_float();
+  *normal = b.randn();
+  *expo = c.randexp();
 }
 const OrcSummary* orc_summary(void* s) { return &((Sim*)s)->sum; }
 int64_t orc_events(void* s, const OrcEvent** p) {
