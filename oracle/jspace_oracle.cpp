@@ -348,6 +348,7 @@ struct Sim {
   // Reference-stream mode (julia_mt.hpp): when set, every draw is taken from the reference's own
   // MersenneTwister in the reference's call order instead of the counter-based draw contract.
   jmt::MersenneTwister* mt = nullptr;
+  std::vector<int64_t> mt_randn_pos;  // pinning aid: where in the raw dSFMT output every randn() call started
   const jmt::IntSet* label_set = nullptr;  // slot layout of Set(1:1000), src/J_Space.jl:366
   // benchmark control (bench.py's time-boxed CPU arm): iterations done so far / stop request
   volatile uint64_t* progress = nullptr;
@@ -916,6 +917,7 @@ void* orc_run_mt(void* g, const OrcParams* p, uint64_t mt_seed, const int32_t* v
   if (!G->is_lattice && p->n_start_cells == 1 && cand.empty()) cand = closeness_argmax(*G);
   s->seed_cells(cand);
   s->run();
+  s->mt_randn_pos = mt.randn_pos;
   s->mt = nullptr;
   s->label_set = nullptr;
   return s;
@@ -927,6 +929,17 @@ void orc_mt_probe(uint64_t mt_seed, double* floats, int n, double* normal, doubl
   for (int i = 0; i < n; ++i) floats[i] = a.rand_float();
   *normal = b.randn();
   *expo = c.randexp();
+}
+// the raw dSFMT output of MersenneTwister(seed): n doubles in [1, 2) as bit patterns, in generation order
+void orc_mt_raw(uint64_t mt_seed, uint64_t* out, int64_t n) {
+  jmt::Variant v;
+  jmt::MersenneTwister m(mt_seed, v);
+  for (int64_t k = 0; k + 1 < n; k += 2) m.ds.next(out + k);
+}
+int64_t orc_mt_randn_pos(void* s, const int64_t** p) {
+  Sim* S = (Sim*)s;
+  *p = S->mt_randn_pos.data();
+  return (int64_t)S->mt_randn_pos.size();
 }
 const OrcSummary* orc_summary(void* s) { return &((Sim*)s)->sum; }
 int64_t orc_events(void* s, const OrcEvent** p) {

@@ -45,7 +45,7 @@ struct DSFMT {
   static constexpr int N = 191, POS1 = 117, SL1 = 19, SR = 12;
   static constexpr uint64_t MSK1 = 0x000ffafffffffb3fULL, MSK2 = 0x000ffdfffc90fffdULL;
   static constexpr uint64_t FIX1 = 0x90014964b32f4329ULL, FIX2 = 0x3b8d12ac548a7c7aULL;
-  static constexpr uint64_t PCV1 = 0x3d84e1ac0dc82880ULL, PCV2 = 0x0000000000000001ULL;
+  static constexpr uint64_t PCV1 = 0x3d84e1ac0dc82880ULL;
   uint64_t st[N + 1][2];
   int pos = 0;  // next state word to regenerate
 
@@ -54,8 +54,8 @@ struct DSFMT {
 
   void init_by_array(const uint32_t* key, int key_length) {
     const int size = (N + 1) * 4, lag = 11, mid = (size - lag) / 2;
-    uint32_t* p = reinterpret_cast<uint32_t*>(&st[0][0]);  // little endian: idxof(i) = i
-    std::memset(st, 0x8b, sizeof st);
+    uint32_t p[(N + 1) * 4];  // the state as 32-bit words (little endian: idxof(i) = i)
+    std::memset(p, 0x8b, sizeof p);
     int count = key_length + 1 > size ? key_length + 1 : size;
     uint32_t r = f1(p[0] ^ p[mid % size] ^ p[(size - 1) % size]);
     p[mid % size] += r;
@@ -88,11 +88,12 @@ struct DSFMT {
       p[i] = r;
       i = (i + 1) % size;
     }
+    std::memcpy(st, p, sizeof p);
     for (int k = 0; k < N; ++k)  // initial_mask
       for (int h = 0; h < 2; ++h) st[k][h] = (st[k][h] & 0x000FFFFFFFFFFFFFULL) | 0x3FF0000000000000ULL;
     // period certification
     uint64_t t0 = st[N][0] ^ FIX1, t1 = st[N][1] ^ FIX2;
-    uint64_t inner = (t0 & PCV1) ^ (t1 & PCV2);
+    uint64_t inner = (t0 & PCV1) ^ (t1 & 1ULL);
     for (int s = 32; s > 0; s >>= 1) inner ^= inner >> s;
     if ((inner & 1) == 0) st[N][1] ^= 1;  // PCV2 & 1 == 1
     pos = 0;
@@ -118,44 +119,14 @@ struct DSFMT {
   }
 };
 
-// ---- ziggurat tables (normal.jl's ki/wi/fi and ke/we/fe) ---------------------------------------------------
+// ---- ziggurat tables (normal.jl's ki/wi/fi and ke/we/fe), regenerated in 50-digit arithmetic from the two
+// published constants by make_zig_tables.py (the strip areas follow from them) ---------------------------------
+#include "zig_tables.inc"
 struct Zig {
-  uint64_t ki[256], ke[256];
-  double wi[256], fi[256], we[256], fe[256];
-  static constexpr double NOR_R = 3.6541528853610088, NOR_INV_R = 0.27366123732975828, NOR_V = 0.00492867323399;
-  static constexpr double EXP_R = 7.69711747013104972, EXP_V = 0.0039496598225815571993;
-  Zig() {
-    const double NM = 2251799813685248.0;  // 2^51
-    const double EM = 4503599627370496.0;  // 2^52
-    double x1 = NOR_R, x;
-    wi[255] = x1 / NM;
-    fi[255] = std::exp(-0.5 * x1 * x1);
-    ki[0] = (uint64_t)(x1 * fi[255] / NOR_V * NM);
-    wi[0] = NOR_V / fi[255] / NM;
-    fi[0] = 1.0;
-    for (int i = 254; i > 0; --i) {
-      x = std::sqrt(-2.0 * std::log(NOR_V / x1 + fi[i + 1]));
-      ki[i + 1] = (uint64_t)(x / x1 * NM);
-      wi[i] = x / NM;
-      fi[i] = std::exp(-0.5 * x * x);
-      x1 = x;
-    }
-    ki[1] = 0;
-    x1 = EXP_R;
-    we[255] = x1 / EM;
-    fe[255] = std::exp(-x1);
-    ke[0] = (uint64_t)(x1 * fe[255] / EXP_V * EM);
-    we[0] = EXP_V / fe[255] / EM;
-    fe[0] = 1.0;
-    for (int i = 254; i > 0; --i) {
-      x = -std::log(EXP_V / x1 + fe[i + 1]);
-      ke[i + 1] = (uint64_t)(x / x1 * EM);
-      we[i] = x / EM;
-      fe[i] = std::exp(-x);
-      x1 = x;
-    }
-    ke[1] = 0;
-  }
+  const uint64_t *ki = ZKI, *ke = ZKE;
+  const double *wi = ZWI, *fi = ZFI, *we = ZWE, *fe = ZFE;
+  static constexpr double NOR_R = 3.6541528853610087963519472518, NOR_INV_R = 1.0 / 3.6541528853610087963519472518;
+  static constexpr double EXP_R = 7.6971174701310497140446280481;
 };
 
 // ---- Base.Dict slot layout for a Set{Int} built by Set(1:n) -------------------------------------------------
@@ -277,6 +248,10 @@ struct MersenneTwister {
   u128 ints[501];
   int idxF = CACHE_F, idxI = 0;
   Variant var;
+  // bookkeeping for the pinning script: position in the raw dSFMT output of the next scalar double
+  int64_t raw_made = 0, vals_base = 0;
+  int64_t raw_pos() const { return idxF == CACHE_F ? raw_made : vals_base + idxF; }
+  std::vector<int64_t> randn_pos;  // raw position of the first double of every randn() call
   static const Zig& zig() { static const Zig z; return z; }
 
   MersenneTwister(uint64_t seed, const Variant& v) : var(v) {
@@ -286,7 +261,7 @@ struct MersenneTwister {
     ds.init_by_array(key, n);
   }
   // -- the vals cache: doubles in [1, 2), as bit patterns
-  void gen_rand() { ds.fill(vals, CACHE_F); idxF = 0; }
+  void gen_rand() { vals_base = raw_made; ds.fill(vals, CACHE_F); raw_made += CACHE_F; idxF = 0; }
   uint64_t pop_bits() {
     if (idxF == CACHE_F) gen_rand();
     return vals[idxF++];
@@ -306,6 +281,7 @@ struct MersenneTwister {
       return;
     }
     ds.fill(A, n2);                                  // dsfmt_fill_array_close1_open2!, bypasses the cache
+    raw_made += n2;
     for (int k = n2; k < n; ++k) A[k] = pop_bits();  // the tail comes from the scalar path
   }
   // -- rand!(r, r.ints): 501 UInt128 out of 52-bit doubles, the missing 12 bits of every half taken from donors
@@ -388,6 +364,7 @@ struct MersenneTwister {
   }
   double randn() {
     const Zig& z = zig();
+    randn_pos.push_back(raw_pos());
     for (;;) {
       const uint64_t r = raw52() & 0x000fffffffffffffULL;
       const int64_t rabs = (int64_t)(r >> 1);

@@ -48,8 +48,8 @@ class OrcParams(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "jspace_oracle.cpp")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("jspace_oracle.cpp", "julia_mt.hpp", "zig_tables.inc")]
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(s) for s in srcs):
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
     return _LIB_PATH
 
