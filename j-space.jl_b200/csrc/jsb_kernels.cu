@@ -53,12 +53,19 @@ enum { PH_REFOLD, PH_DRAWS, PH_CLASS, PH_EVAL, PH_TIME, PH_BIRTH, PH_DEATH, PH_M
 __device__ long long g_sub[8];  // sub-phase cycle totals of one profiled replicate (lane 0)
 #define SUB_T0() long long _s0 = clock64()
 #define SUB_ADD(k) do { long long _s1 = clock64(); if ((threadIdx.x & 31) == 0) g_sub[k] += _s1 - _s0; _s0 = _s1; } while (0)
+// deferred-mode phases (one profiled replicate at a time): cycles and counts, lane 0
+enum { DP_EVAL, DP_HELP, DP_COMMIT, DP_DEATH, DP_BIRTH, DP_MIGR, DP_BOOK, DP_APPROX, DP_SERVE, DP_SV_A, DP_SV_WALK, DP_SV_CHAIN, DP_RESYNC, DP_N };
+__device__ long long g_dp[DP_N], g_dpn[DP_N];
+#define DP_T0() long long _d0 = clock64()
+#define DP_ADD(k) do { long long _d1 = clock64(); if ((threadIdx.x & 31) == 0) { g_dp[k] += _d1 - _d0; g_dpn[k]++; } _d0 = _d1; } while (0)
 #else
 #define PROF_DECL
 #define PROF_T0()
 #define PROF_ADD(ph)
 #define SUB_T0()
 #define SUB_ADD(k)
+#define DP_T0()
+#define DP_ADD(k)
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -1908,12 +1915,23 @@ __device__ __noinline__ void approx_update(Ctx<T>& X, Rep& r, uint32_t S_old, ui
   const uint32_t sB = X.sB;
   const uint32_t lo = i0 < i1 ? i0 : i1;
   if (lo != kNone) {
-    for (uint32_t i = lo + (uint32_t)X.lane; i < S_old; i += 32) {
-      double v = lds_f64(sB + i * 8u);
-      if (i >= i0) v = v + a0;
-      if (i >= i1) v = v + a1;
-      // the class search orders the entries by their bit patterns: never negative (true values are >= 0)
-      sts_f64(sB + i * 8u, v < 0.0 ? 0.0 : v);
+    // eight entries per lane in flight (the shared-memory accessors are ordered asm statements: one at a time
+    // they would each pay the full load latency)
+    for (uint32_t base = lo + (uint32_t)X.lane; base < S_old; base += 256u) {
+      double v[8];
+#pragma unroll
+      for (uint32_t k = 0; k < 8u; ++k) {
+        const uint32_t i = base + 32u * k;
+        v[k] = i < S_old ? lds_f64(sB + i * 8u) : 0.0;
+      }
+#pragma unroll
+      for (uint32_t k = 0; k < 8u; ++k) {
+        const uint32_t i = base + 32u * k;
+        if (i >= i0) v[k] = v[k] + a0;
+        if (i >= i1) v[k] = v[k] + a1;
+        // the class search orders the entries by their bit patterns: never negative (true values are >= 0)
+        if (i < S_old) sts_f64(sB + i * 8u, v[k] < 0.0 ? 0.0 : v[k]);
+      }
     }
   }
   __syncwarp();
@@ -1959,13 +1977,25 @@ __device__ __noinline__ void deferred_serve(Ctx<T>& X, const Rep& r, const Pend&
   const int lane = X.lane;
   const DevPoint& P = *X.P;
   double lam = 0.0;  // lane e: exact λ after event e
+  DP_T0();
   if (ne) {
     const uint32_t S = r.S;  // clones at the end of the batch
     double* __restrict__ gw = X.g_w;
-    // w_i = α_i·n_i with the sizes at the END of the batch (:693), zero-padded to a multiple of eight
-    const uint32_t S8 = (S + 7u) & ~7u;
-    for (uint32_t i = (uint32_t)lane; i < S8; i += 32)
-      gw[i] = i < S ? X.c_alpha[i] * (double)lds_tab<T>(X.sLen, i) : 0.0;
+    // w_i = α_i·n_i with the sizes at the END of the batch (:693), zero-padded to a multiple of sixteen
+    const uint32_t S16 = (S + 15u) & ~15u;
+    for (uint32_t base = (uint32_t)lane; base < S16; base += 256u) {
+      double a[8];
+#pragma unroll
+      for (uint32_t k = 0; k < 8u; ++k) {
+        const uint32_t i = base + 32u * k;
+        a[k] = i < S ? ldg_keep_f64(X.c_alpha + i) : 0.0;
+      }
+#pragma unroll
+      for (uint32_t k = 0; k < 8u; ++k) {
+        const uint32_t i = base + 32u * k;
+        if (i < S16) gw[i] = i < S ? a[k] * (double)lds_tab<T>(X.sLen, i) : 0.0;
+      }
+    }
     // bitmap of the clones some event of the batch touched (1024 bits in the dt staging area)
     uint32_t* bm = reinterpret_cast<uint32_t*>(X.B + kSmemTable);
     bm[lane] = 0;
@@ -1973,17 +2003,20 @@ __device__ __noinline__ void deferred_serve(Ctx<T>& X, const Rep& r, const Pend&
     if ((uint32_t)lane < ne)
       for (uint32_t k = 0; k < pe.n_upd; ++k) atomicOr(&bm[pe.ui[k] >> 5], 1u << (pe.ui[k] & 31u));
     __syncwarp();
+    DP_ADD(DP_SV_A);
     // lane e's own left fold over the sizes as they were after event e: n_i(e) = n_i(end) - (what the later
-    // events of the batch did to clone i); a clone born later has size 0 for lane e (and adds +0.0)
+    // events of the batch did to clone i); a clone born later has size 0 for lane e (and adds +0.0).
+    // Blocks of eight, the next block requested before the current one is added.
     double acc = 0.0;
-    for (uint32_t b8 = 0; b8 < S8; b8 += 8u) {
-      const uint32_t tb = (bm[b8 >> 5] >> (b8 & 31u)) & 0xFFu;
-      double v[8];
+    double v[8], w[8];
+    const double2* g2 = reinterpret_cast<const double2*>(gw);
 #pragma unroll
-      for (uint32_t j = 0; j < 8u; j += 2u) {
-        const double2 q = *reinterpret_cast<const double2*>(gw + b8 + j);
-        v[j] = q.x; v[j + 1] = q.y;
-      }
+    for (uint32_t j = 0; j < 4u; ++j) { const double2 q = g2[j]; v[2 * j] = q.x; v[2 * j + 1] = q.y; }
+    for (uint32_t b8 = 0; b8 < S16; b8 += 8u) {
+      const uint32_t nb8 = b8 + 8u < S16 ? b8 + 8u : b8;  // clamped prefetch
+#pragma unroll
+      for (uint32_t j = 0; j < 4u; ++j) { const double2 q = g2[(nb8 >> 1) + j]; w[2 * j] = q.x; w[2 * j + 1] = q.y; }
+      const uint32_t tb = (bm[b8 >> 5] >> (b8 & 31u)) & 0xFFu;
       if (tb) {
 #pragma unroll
         for (uint32_t j = 0; j < 8u; ++j) {
@@ -2002,36 +2035,71 @@ __device__ __noinline__ void deferred_serve(Ctx<T>& X, const Rep& r, const Pend&
       }
 #pragma unroll
       for (uint32_t j = 0; j < 8u; ++j) acc = acc + v[j];
+#pragma unroll
+      for (uint32_t j = 0; j < 8u; ++j) v[j] = w[j];
     }
     const double death = P.rate_death * (double)pe.n;     // :696
     const double M = P.rate_migration * (double)pe.n;     // :697
     const double bd = acc + death;
     lam = bd + M;                                          // :698
+    DP_ADD(DP_SV_WALK);
   }
-  // the exact clock: t += e·(1/λ) over every committed iteration, with the rate of the state it ran in
-  double t = t_exact, lam_prev = lam_exact;
-  uint32_t pos = 0;
-  for (uint32_t e = 0; e <= ne; ++e) {
-    const uint32_t cnt = e < ne ? __shfl_sync(FULL, pe.m, (int)e) : tail_m;
-    const double theta = 1.0 / lam_prev;  // :699, the same expression the fold uses
-    for (uint32_t done = 0; done < cnt; done += 32) {
-      const uint32_t left = cnt - done;
-      const double ex = (uint32_t)lane < left ? ring[pos + done + (uint32_t)lane] : 0.0;
-      t = time_chain(X.sDt, lane, t, ex * theta, left >= 32u ? 31u : left - 1u);  // :701
+  // The exact clock: t += e·(1/λ) over every committed iteration, with the rate of the state it ran in (:699,
+  // :701).  One pass over the ring, sixteen exponentials requested ahead of the sixteen being added (every lane
+  // runs the same chain on broadcast loads); at the end of a segment the event's log rows get their time and
+  // the rate of the next segment takes over.
+  {
+    const uint32_t total = [&]() {
+      uint32_t mine = (uint32_t)lane < ne ? pe.m : 0u;
+      for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(FULL, mine, d);
+      return mine + tail_m;
+    }();
+    double t = t_exact;
+    double theta = 1.0 / lam_exact;  // :699, the same expression the fold uses
+    uint32_t e = 0;
+    uint32_t seg_end = ne ? __shfl_sync(FULL, pe.m, 0) : total;  // first iteration index after segment e
+    const double2* r2 = reinterpret_cast<const double2*>(ring);   // the ring starts on a 16-byte boundary
+    const uint32_t total16 = (total + 15u) & ~15u;                // reads up to 15 entries past the end (allocated)
+    double a[16], bq[16];
+    if (total) {
+#pragma unroll
+      for (uint32_t j = 0; j < 8u; ++j) { const double2 q = r2[j]; a[2 * j] = q.x; a[2 * j + 1] = q.y; }
     }
-    pos += cnt;
-    if (e < ne) {
+    for (uint32_t k0 = 0; k0 < total16; k0 += 16u) {
+      const uint32_t nk = k0 + 16u < total16 ? k0 + 16u : k0;
+#pragma unroll
+      for (uint32_t j = 0; j < 8u; ++j) { const double2 q = r2[(nk >> 1) + j]; bq[2 * j] = q.x; bq[2 * j + 1] = q.y; }
+#pragma unroll
+      for (uint32_t j = 0; j < 16u; ++j) {
+        const uint32_t k = k0 + j;
+        while (k == seg_end && e < ne) {  // the event of segment e happened at time t
+          const uint32_t n_rows = __shfl_sync(FULL, pe.n_rows, (int)e);
+          const uint32_t q0 = __shfl_sync(FULL, pe.row[0], (int)e), q1 = __shfl_sync(FULL, pe.row[1], (int)e),
+                         q2 = __shfl_sync(FULL, pe.row[2], (int)e);
+          if ((uint32_t)lane < n_rows)
+            *reinterpret_cast<double*>(X.A->log_pool + (lane == 0 ? q0 : (lane == 1 ? q1 : q2))) = t;
+          theta = 1.0 / __shfl_sync(FULL, lam, (int)e);
+          ++e;
+          seg_end += e < ne ? __shfl_sync(FULL, pe.m, (int)e) : tail_m;
+        }
+        if (k < total) t = t + a[j] * theta;  // :701
+      }
+#pragma unroll
+      for (uint32_t j = 0; j < 16u; ++j) a[j] = bq[j];
+    }
+    while (e < ne) {  // events whose segment ends exactly at the end of the ring
       const uint32_t n_rows = __shfl_sync(FULL, pe.n_rows, (int)e);
-      const uint32_t r0 = __shfl_sync(FULL, pe.row[0], (int)e), r1 = __shfl_sync(FULL, pe.row[1], (int)e),
-                     r2 = __shfl_sync(FULL, pe.row[2], (int)e);
+      const uint32_t q0 = __shfl_sync(FULL, pe.row[0], (int)e), q1 = __shfl_sync(FULL, pe.row[1], (int)e),
+                     q2 = __shfl_sync(FULL, pe.row[2], (int)e);
       if ((uint32_t)lane < n_rows)
-        *reinterpret_cast<double*>(X.A->log_pool + (lane == 0 ? r0 : (lane == 1 ? r1 : r2))) = t;
-      lam_prev = __shfl_sync(FULL, lam, (int)e);
+        *reinterpret_cast<double*>(X.A->log_pool + (lane == 0 ? q0 : (lane == 1 ? q1 : q2))) = t;
+      ++e;
     }
+    if (ne) lam_exact = __shfl_sync(FULL, lam, (int)ne - 1);
+    t_exact = t;
   }
-  lam_exact = lam_prev;
-  t_exact = t;
   __syncwarp();
+  DP_ADD(DP_SV_CHAIN);
 }
 
 // Runs rounds on the approximate table and clock until the exact state is needed again: a time that matters
@@ -2060,7 +2128,9 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
   if (lane == 0) atomicAdd(A.work_counter + 2, 1ull);  // statistics: entries into deferred mode (JSB_TIMING)
 
   auto serve = [&]() {
+    DP_T0();
     deferred_serve(X, r, pe, ne, seg_m, ring, lam_exact, t_exact);
+    DP_ADD(DP_SERVE);
     r.t = t_exact;
     ring_n = 0; ne = 0; seg_m = 0;
   };
@@ -2070,8 +2140,10 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
     if (ne == 32u || ring_n + 32u * (1u + (uint32_t)kMaxLook) > ring_cap) serve();
     if (dec_events >= kApproxResync) {         // re-base the approximate table on the exact one
       serve();
+      DP_T0();
       r.dirty_from = 0;
       refold(X, r);
+      DP_ADD(DP_RESYNC);
       lam_exact = r.lambda;
       r.guard = ((P.quirks & JSB_QUIRK_DEBUG_WIDE_GUARD) ? 1e-3 : 2.0 * kGuardEps) * r.lambda;
       dec_events = 0;
@@ -2106,10 +2178,12 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
 
     double ev[kMaxSub];
     uint32_t effm[kMaxSub], cls[kMaxSub], xx[kMaxSub], cell[kMaxSub], pos[kMaxSub];
+    DP_T0();
     if (!batch_eval<T, 1>(X, r, false, FULL, ev, effm, cls, xx, cell, pos, true)) {
       wait_acks();  // a draw inside the guard band: the exact loop decides this round
       break;
     }
+    DP_ADD(DP_EVAL);
     bool found = effm[0] != 0;
     uint32_t jE = found ? (uint32_t)__ffs(effm[0]) - 1u : 31u;
 
@@ -2148,6 +2222,7 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
         from_helper = (int)h;
       }
     }
+    DP_ADD(DP_HELP);
     // keep the unit exponentials of the committed iterations, in iteration order
     ring[ring_n + (uint32_t)lane] = ev[0];
     for (uint32_t h = 0; h * 32u < adv; ++h) ring[ring_n + 32u * (h + 1u) + (uint32_t)lane] = M->res[h].dt[lane];
@@ -2157,6 +2232,7 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
     r.it += m_commit;
     r.t = t1;  // approximate; the log records written below get the exact time when the batch is served
     __syncwarp();
+    DP_ADD(DP_COMMIT);
 
     // ---- the event, and what it does to the clone sizes -----------------------------------------
     if (!found) continue;
@@ -2178,15 +2254,17 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
       }
       ej.occ = (ej.cls < r.S && P.rule != JSB_RULE_CONTACT) ? (uint32_t)X.clone[ej.pos] : 0u;
       ej.effective = true;
-      if (ej.cls == r.S + 1) apply_migration(X, r, ej);
+      if (ej.cls == r.S + 1) { apply_migration(X, r, ej); DP_ADD(DP_MIGR); }
       else if (ej.cls == r.S) {
         const uint32_t cl = apply_death(X, r, ej);
         u_i0 = cl - 1u; u_a0 = -X.c_alpha[cl - 1u];
+        DP_ADD(DP_DEATH);
       } else {
         // requested before the event so that the loads are back when it is done
         u_i1 = ej.cls; u_a1 = X.c_alpha[ej.cls];
         if (ej.occ) { u_i0 = ej.occ - 1u; u_a0 = -X.c_alpha[ej.occ - 1u]; }
         keep_going = apply_birth(X, r, ej);
+        DP_ADD(DP_BIRTH);
       }
     }
     // ---- remember what this event did; move the approximate table --------------------------------
@@ -2216,12 +2294,14 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
     }
     ++ne;
     seg_m = 0;
+    DP_ADD(DP_BOOK);
     if (changed) {
       const double new_alpha = has_new ? X.c_alpha[S_old] : 0.0;
       Ctx<T> xc = X; Rep rc = r;
       approx_update(xc, rc, S_old, u_i0, u_a0, u_i1, u_a1, has_new, new_alpha);
       r = rc; X.search_top = xc.search_top;
       ++dec_events;
+      DP_ADD(DP_APPROX);
     }
     if (!keep_going || r.status == JSB_ST_INTERNAL) { finished = true; break; }
   }
@@ -2486,6 +2566,10 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, c
 #ifdef JSB_PROFILE
   if (lane == 0 && (X.local_idx < 2 || r.it > 6000000ull)) {
     printf("sub-phases: refold A %lld B %lld tail %lld\n", g_sub[0], g_sub[1], g_sub[2]);
+    printf("deferred: eval %lld/%lld help %lld commit %lld | death %lld/%lld birth %lld/%lld migr %lld/%lld | book %lld approx %lld/%lld | serve %lld/%lld (A %lld walk %lld chain %lld) resync %lld/%lld\n",
+           g_dp[DP_EVAL], g_dpn[DP_EVAL], g_dp[DP_HELP], g_dp[DP_COMMIT], g_dp[DP_DEATH], g_dpn[DP_DEATH], g_dp[DP_BIRTH], g_dpn[DP_BIRTH],
+           g_dp[DP_MIGR], g_dpn[DP_MIGR], g_dp[DP_BOOK], g_dp[DP_APPROX], g_dpn[DP_APPROX], g_dp[DP_SERVE], g_dpn[DP_SERVE],
+           g_dp[DP_SV_A], g_dp[DP_SV_WALK], g_dp[DP_SV_CHAIN], g_dp[DP_RESYNC], g_dpn[DP_RESYNC]);
     printf("rep %lld it %llu rounds %lld eff %u S %u n %u | refold %lld/%lld (elems %lld) draws %lld/%lld class %lld eval %lld time %lld | birth %lld/%lld death %lld/%lld migr %lld/%lld exc %lld\n",
            (long long)X.local_idx, (unsigned long long)r.it, prof_n[PH_EVAL], r.n_eff, r.S, r.n, prof_c[PH_REFOLD], prof_n[PH_REFOLD], prof_fold,
            prof_c[PH_DRAWS], prof_n[PH_DRAWS], prof_c[PH_CLASS], prof_c[PH_EVAL], prof_c[PH_TIME], prof_c[PH_BIRTH],
