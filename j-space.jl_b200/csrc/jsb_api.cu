@@ -654,12 +654,16 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
         if ((1 + kMaxHelp) * per_sm < wpb) wpb = (int)((1 + kMaxHelp) * per_sm);
         grid = (int)std::min<int64_t>(n_local, sms);
         a.static_map = (uint64_t)n_local < (uint64_t)grid * wpb ? 1u : 0u;
-        a.helpers = 1u;
+        a.clock_max_busy = 3;
+        if (const char* e = std::getenv("JSB_CLOCK_MAX_BUSY")) a.clock_max_busy = (uint32_t)std::atoi(e);  // tuning hook
+        a.helpers = std::getenv("JSB_NO_CLOCK") ? 3u : 1u;  // bit 1: lookahead only, no clock helper (debug)
       }
       if (!fast_mode) {
         a.dec_min_clones = kDecMinClones;
+        a.defer_min_clones = kDeferMinClones;
         if (const char* e = std::getenv("JSB_DEC_MIN_CLONES")) a.dec_min_clones = (uint32_t)std::max(1, std::atoi(e));  // tuning hook
-        a.defer = std::getenv("JSB_NO_CLOCK") ? 0u : 1u;  // JSB_NO_CLOCK=1: exact fold and clock after every event (debug, A/B)
+        if (const char* e = std::getenv("JSB_DEFER_MIN_CLONES")) a.defer_min_clones = (uint32_t)std::max(1, std::atoi(e));  // tuning hook
+        a.defer = (std::getenv("JSB_NO_CLOCK") || std::getenv("JSB_NO_DEFER")) ? 0u : 1u;  // exact fold and clock after every event (debug, A/B)
       }
     }
     if (const char* e = std::getenv("JSB_DEBUG_GRID")) {  // debug: pack the replicates on fewer SMs (contention measurements)

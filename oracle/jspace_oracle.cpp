@@ -905,7 +905,7 @@ void* orc_run_mt(void* g, const OrcParams* p, uint64_t mt_seed, const int32_t* v
   jmt::Variant v;
   if (variant) {
     v.set_slots = variant[0]; v.sizehint_mode = variant[1]; v.hash_float = variant[2] != 0;
-    v.range_fast = variant[3] != 0; v.set_ndl = variant[4] != 0; v.int_fill_tail = variant[5];
+    v.range_fast = variant[3] != 0; v.set_ndl = variant[4] != 0; v.int_fill_tail = variant[5]; v.test_float_start = variant[6]; v.refill_pad = variant[7];
   }
   jmt::MersenneTwister mt(mt_seed, v);
   jmt::IntSet labels = jmt::IntSet::range(1000, v);

@@ -38,6 +38,9 @@ struct Variant {
   bool range_fast = true;   // single rand(rng, a:b): SamplerRangeFast (true) or SamplerRangeNDL (false)
   bool set_ndl = true;      // slot draws inside rand(::Set): NDL on UInt64 (true) or Fast on UInt52Raw (false)
   int int_fill_tail = 2;    // doubles taken from the scalar cache at the end of a big array fill
+  int refill_pad = 0;         // pinning aid: scalar doubles consumed by an integer-cache refill, relative to the model
+  int test_float_start = -1;  // pinning aid: >= 0 -> the scalar doubles are raw[test_float_start...] contiguously and the
+                              // integer cache draws from a separate generator (never touches the scalar stream)
 };
 
 // ---- dSFMT-19937 ------------------------------------------------------------------------------------------
@@ -259,6 +262,12 @@ struct MersenneTwister {
     int n = 0;
     do { key[n++] = (uint32_t)seed; seed >>= 32; } while (seed != 0);  // make_seed
     ds.init_by_array(key, n);
+    if (v.test_float_start >= 0) {
+      uint64_t tmp[2];
+      for (int k = 0; k + 1 < v.test_float_start; k += 2) ds.next(tmp);
+      raw_made = v.test_float_start & ~1;
+      if (v.test_float_start & 1) { gen_rand(); idxF = 1; }
+    }
   }
   // -- the vals cache: doubles in [1, 2), as bit patterns
   void gen_rand() { vals_base = raw_made; ds.fill(vals, CACHE_F); raw_made += CACHE_F; idxF = 0; }
@@ -286,12 +295,17 @@ struct MersenneTwister {
   }
   // -- rand!(r, r.ints): 501 UInt128 out of 52-bit doubles, the missing 12 bits of every half taken from donors
   void fill_ints() {
-    int n = 501;
+    if (var.test_float_start >= 0) {  // pinning aid: content irrelevant, scalar stream untouched
+      for (int k = 0; k < 501; ++k) ints[k] = ((u128)0x9E3779B97F4A7C15ULL * (u128)(k + 1 + raw_made)) << 17;
+      idxI = CACHE_I_BYTES;
+      return;
+    }
+    int n = 501, i = n;
     uint64_t* F = reinterpret_cast<uint64_t*>(ints);
     for (;;) {
-      fill_floats(F, 2 * n);
+      fill_floats(F, 2 * i);  // the first pass fills everything, later passes only the donors just used up
       if (n < 5) break;
-      int i = 0;
+      i = 0;
       while (n - i >= 5) {
         const u128 u = ints[i++];          // A[i += 1]
         ints[n - 1] ^= u << 48;            // A[n]
@@ -305,8 +319,10 @@ struct MersenneTwister {
       if (CACHE_F - idxF < 2) gen_rand();                 // reserve(r, 2) discards a single leftover double
       const u128 hi = (u128)raw52(), lo = (u128)raw52();  // rand_ui2x52_raw: first pop is the high half
       const u128 u = (hi << 64) | lo;
-      for (int i = 1; i <= n; ++i) ints[i - 1] ^= u << (12 * i);
+      for (int k = 1; k <= n; ++k) ints[k - 1] ^= u << (12 * k);
     }
+    if (var.refill_pad > 0) for (int k = 0; k < var.refill_pad; ++k) (void)pop_bits();
+    if (var.refill_pad < 0 && idxF + var.refill_pad >= 0) idxF += var.refill_pad;
     idxI = CACHE_I_BYTES;
   }
   uint64_t rand_u64() {

@@ -26,7 +26,7 @@ import oracle as O  # noqa: E402
 SHIPPED = dict(method=1, Tf=200.0, rate_birth=0.2, rate_death=0.01, rate_migration=0.01, mu_driver=0.01, adv_mean=0.4,
                adv_std=0.1, rule="contact", n_start_cells=1, t_bottleneck=[50.0, 150.0], ratio_bottleneck=[0.8, 0.8],
                t_snapshot=[10.0, 20.0])
-DEFAULT_VARIANT = (0, 2, 1, 1, 1, 2)  # set_slots, sizehint_mode, hash_float, range_fast, set_ndl, int_fill_tail
+DEFAULT_VARIANT = (0, 2, 0, 1, 1, 2, -1, 0)  # set_slots, sizehint_mode, hash_float, range_fast, set_ndl, int_fill_tail
 
 
 def read_driverlist(path):
@@ -85,7 +85,7 @@ def main():
     ref = read_driverlist(path)
     O.build()
     if "--search" in sys.argv:
-        for var in itertools.product((0, 1024, 2048, 4096), (0, 1, 2), (0, 1), (0, 1), (0, 1), (0, 2)):
+        for var in itertools.product((0, 1024, 2048, 4096), (0, 1, 2), (0, 1), (0, 1), (0, 1), (0, 2), (-1,), (0,)):
             ours, s = run_mt(variant=var)
             n_g, n_f, first = compare(ours, ref)
             if n_g > 1:
