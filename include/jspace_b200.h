@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JSB_ABI_VERSION 1
+#define JSB_ABI_VERSION 2
 
 /* ---- error codes -------------------------------------------------------------------- */
 #define JSB_OK 0
@@ -196,9 +196,15 @@ typedef struct jsb_run_opts {
    * depend on how an ensemble is sharded over GPUs/ranks.  g_end = 0 means "all".        */
   int64_t g_begin;
   int64_t g_end;
-  int32_t device;         /* CUDA device ordinal                                          */
+  int32_t device;         /* CUDA device ordinal (used when n_devices == 0)               */
   int32_t warps_per_sm;   /* 0 = library default                                          */
-  uint64_t log_pool_bytes; /* event-log pool size; 0 = library default                    */
+  uint64_t log_pool_bytes; /* event-log pool size per device; 0 = library default         */
+  /* Several GPUs of one box in ONE call: the replicate range [g_begin, g_end) is
+   * cut into n_devices contiguous shards, one host thread + stream per device; replicate g still
+   * uses Philox stream g, so the result is the same as on one device.  n_devices == 0: `device`. */
+  int32_t n_devices;
+  int32_t reserved;
+  const int32_t* devices; /* [n_devices] CUDA device ordinals, all different                  */
 } jsb_run_opts;
 
 typedef struct jsb_graph jsb_graph;
@@ -231,8 +237,15 @@ int jsb_graph_neighbors(const jsb_graph* g, int64_t site, int64_t* out, int cap)
 void jsb_graph_free(jsb_graph* g);
 
 /* ---- run: replaces both simulate_evolution methods, for an ensemble -------------------- */
+/* Thread safety: jsb_run is blocking and re-entrant.  Calls that use the same device are serialised
+ * inside the library (one launch configuration and one set of cached device buffers per device);
+ * calls on different devices run concurrently.  A jsb_graph may be shared between threads: its
+ * per-device copies are created under a lock.  Results are independent objects.               */
 int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t reps_per_point,
             const jsb_run_opts* opts, jsb_result** out);
+/* Device buffers (workspace, log pool, outputs) and the pinned staging block are kept between calls;
+ * jsb_trim() releases them (every device).                                                     */
+void jsb_trim(void);
 /* Same, but the per-replicate outputs stay on the device and only timing is returned
  * (used by benchmarks to separate kernel time from copies).  elapsed_ms = CUDA-event time
  * of the simulation kernel alone.                                                         */

@@ -1934,12 +1934,15 @@ __device__ __noinline__ void approx_update(Ctx<T>& X, Rep& r, uint32_t S_old, ui
   const uint32_t sB = X.sB;
   const uint32_t lo = i0 < i1 ? i0 : i1;
   if (lo != kNone) {
+    // plain loads and stores (the ordered asm accessors would serialise the iterations on the load latency)
+    double* __restrict__ Bt = X.B;
+#pragma unroll 4
     for (uint32_t i = lo + (uint32_t)X.lane; i < S_old; i += 32) {
-      double v = lds_f64(sB + i * 8u);
+      double v = Bt[i];
       if (i >= i0) v = v + a0;
       if (i >= i1) v = v + a1;
       // the class search orders the entries by their bit patterns: never negative (true values are >= 0)
-      sts_f64(sB + i * 8u, v < 0.0 ? 0.0 : v);
+      Bt[i] = v < 0.0 ? 0.0 : v;
     }
   }
   __syncwarp();
@@ -2459,7 +2462,8 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, c
 
   // deferred mode needs room for the unit exponentials of a batch in the excision scratch array
   const bool ring_fits = nv / 4u >= 64u * (1u + (uint32_t)kMaxLook);
-  const bool dec_allowed = A.defer != 0 && !force_exact && width == 32u && A.pilot_iters == 0 && ring_fits;
+  const bool dec_allowed = (A.defer != 0 || (P.quirks & JSB_QUIRK_DEBUG_DECOUPLE) != 0) && !force_exact && width == 32u &&
+                           A.pilot_iters == 0 && ring_fits;
   const bool clk_allowed = M != nullptr && (A.helpers & 2u) == 0 && A.pilot_iters == 0 && ring_fits;
   const bool debug_dec = (P.quirks & JSB_QUIRK_DEBUG_DECOUPLE) != 0;
   const uint32_t dec_min_clones = debug_dec ? 1u : (A.dec_min_clones < A.defer_min_clones ? A.dec_min_clones : A.defer_min_clones);

@@ -76,6 +76,7 @@ class RunOpts(C.Structure):
         ("size", C.c_uint32), ("flags", C.c_uint32), ("seed", C.c_uint64),
         ("g_begin", C.c_int64), ("g_end", C.c_int64),
         ("device", C.c_int32), ("warps_per_sm", C.c_int32), ("log_pool_bytes", C.c_uint64),
+        ("n_devices", C.c_int32), ("reserved", C.c_int32), ("devices", C.POINTER(C.c_int32)),
     ]
 
 
@@ -96,6 +97,7 @@ SIGNATURES = {
     "jsb_graph_neighbors": (C.c_int, [_VP, C.c_int64, _VP, C.c_int]),
     "jsb_graph_free": (None, [_VP]),
     "jsb_run": (C.c_int, [_VP, C.POINTER(Params), C.c_int64, C.c_int64, C.POINTER(RunOpts), _PVP]),
+    "jsb_trim": (None, []),
     "jsb_result_kernel_ms": (C.c_int, [_VP, C.POINTER(C.c_double)]),
     "jsb_result_launches": (C.c_int, [_VP, C.POINTER(C.c_int64)]),
     "jsb_result_count": (C.c_int64, [_VP]),
@@ -134,7 +136,7 @@ def lib():
             f = getattr(L, name)
             f.restype = res
             f.argtypes = args
-        if L.jsb_abi_version() != 1:
+        if L.jsb_abi_version() != 2:
             raise ImportError("libjspace_b200.so ABI version mismatch")
         _lib = L
     return _lib

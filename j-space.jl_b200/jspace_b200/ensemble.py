@@ -225,8 +225,9 @@ class EnsembleResult:
 
 def run_ensemble(graph: Graph, points, reps_per_point: int = 1, *, seed: int = 1234, flags: int = 0,
                  g_begin: int = 0, g_end: int = 0, device: int = 0, warps_per_sm: int = 0,
-                 log_pool_bytes: int = 0) -> EnsembleResult:
-    """jsb_run: replicate g = point*reps_per_point + r uses Philox stream g."""
+                 log_pool_bytes: int = 0, devices=None) -> EnsembleResult:
+    """jsb_run: replicate g = point*reps_per_point + r uses Philox stream g.  `devices`: several GPUs of the
+    box in one call (the replicate range is cut into contiguous shards, one per device)."""
     if isinstance(points, Point):
         points = [points]
     arr = (L.Params * len(points))(*[p.to_struct() for p in points])
@@ -238,6 +239,11 @@ def run_ensemble(graph: Graph, points, reps_per_point: int = 1, *, seed: int = 1
     o.device = int(device)
     o.warps_per_sm = int(warps_per_sm)
     o.log_pool_bytes = int(log_pool_bytes)
+    dev_arr = None
+    if devices:
+        dev_arr = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        o.n_devices = len(devices)
+        o.devices = C.cast(dev_arr, C.POINTER(C.c_int32))
     h = C.c_void_p()
     L.check(L.lib().jsb_run(graph._h, arr, len(points), int(reps_per_point), C.byref(o), C.byref(h)))
     return EnsembleResult(h, graph, flags)

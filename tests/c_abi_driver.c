@@ -1,8 +1,8 @@
 /* c_abi_driver.c — exercises libjspace_b200.so through the C ABI exactly the way the Julia wrapper
  * (j-space.jl_b200/julia/JSpaceB200.jl) does: same calls, same argument types, same order, same
  * ownership (one jsb_graph handle shared by the input graph and every result graph, freed once).
- * Test infrastructure; built and run by tests/test_c_driver_gpu.py (also once under
- * compute-sanitizer).  No Python, no ctypes: plain C against include/jspace_b200.h.
+ * Test infrastructure; built and run by tests/test_c_driver_gpu.py.  No Python, no ctypes: plain C
+ * against include/jspace_b200.h.
  *
  *   c_abi_driver <libdir-unused>            runs the sequence, prints "C-ABI-DRIVER OK <checksum>"
  */

@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported_and_bound(jsb):
     for s in syms:
         assert hasattr(lib, s), s
     assert sorted(L.SIGNATURES) == syms  # the ctypes binding covers exactly the header
-    assert lib.jsb_abi_version() == 1
+    assert lib.jsb_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(jsb, tmp_path):
