@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
+#include <map>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -116,25 +117,28 @@ struct jsb_graph {
   std::vector<uint32_t> rowptr, colidx;  // csr, 0-based
   bool have_cand = false;
   std::vector<int64_t> cand;  // 1-based
-  // device copies (one device at a time; re-uploaded when the device changes)
-  int dev = -1;
-  uint32_t *d_rowptr = nullptr, *d_colidx = nullptr, *d_cand = nullptr;
-  uint32_t d_ncand = 0;
-  bool d_cand_valid = false;
+  // One copy per device, created on first use under `mu` (a graph may be shared by threads that run on
+  // different devices); the seed candidates are re-uploaded when they change (cand_version).
+  struct DevCopy {
+    uint32_t *d_rowptr = nullptr, *d_colidx = nullptr, *d_cand = nullptr;
+    uint32_t d_ncand = 0;
+    uint64_t cand_version = ~0ull;
+  };
+  std::mutex mu;
+  std::map<int, DevCopy> dev;
+  uint64_t cand_version = 0;
 
-  void drop_device() {
-    if (dev >= 0) {
-      int cur = 0;
-      cudaGetDevice(&cur);
-      cudaSetDevice(dev);
-      cudaFree(d_rowptr);
-      cudaFree(d_colidx);
-      cudaFree(d_cand);
-      cudaSetDevice(cur);
+  void drop_devices() {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& kv : dev) {
+      cudaSetDevice(kv.first);
+      cudaFree(kv.second.d_rowptr);
+      cudaFree(kv.second.d_colidx);
+      cudaFree(kv.second.d_cand);
     }
-    d_rowptr = d_colidx = d_cand = nullptr;
-    dev = -1;
-    d_cand_valid = false;
+    dev.clear();
+    cudaSetDevice(cur);
   }
 };
 
@@ -344,7 +348,7 @@ int jsb_graph_seed_candidates(jsb_graph* g, const int64_t** sites, int64_t* n) {
   if (!g->have_cand) {
     closeness_argmax(*g, g->cand);
     g->have_cand = true;
-    g->d_cand_valid = false;
+    g->cand_version++;
   }
   *sites = g->cand.data();
   *n = (int64_t)g->cand.size();
@@ -355,9 +359,10 @@ int jsb_graph_set_seed_candidates(jsb_graph* g, const int64_t* sites, int64_t n)
   if (!g || (n > 0 && !sites) || n < 0) return fail(JSB_EINVAL, "null argument");
   for (int64_t i = 0; i < n; ++i)
     if (sites[i] < 1 || sites[i] > g->nv) return fail(JSB_EINVAL, "seed candidate %lld is outside 1..nv", (long long)sites[i]);
+  std::lock_guard<std::mutex> lk(g->mu);
   g->cand.assign(sites, sites + n);
   g->have_cand = true;
-  g->d_cand_valid = false;
+  g->cand_version++;
   return JSB_OK;
 }
 
@@ -372,7 +377,7 @@ int jsb_graph_neighbors(const jsb_graph* g, int64_t site, int64_t* out, int cap)
 
 void jsb_graph_free(jsb_graph* g) {
   if (!g) return;
-  g->drop_device();
+  g->drop_devices();
   delete g;
 }
 
@@ -401,10 +406,27 @@ struct jsb_result {
   std::vector<int32_t> snap_count;
   double kernel_ms = 0.0;
   int64_t launches = 0;
+  // a multi-device call: one result per device shard (this object then only holds the merged summaries)
+  std::vector<jsb_result*> parts;
+  std::vector<int64_t> part_off;  // first local index of every part
   ~jsb_result();
 };
 
-jsb_result::~jsb_result() { pinned_give(pinned, pinned_bytes); }
+jsb_result::~jsb_result() {
+  pinned_give(pinned, pinned_bytes);
+  for (jsb_result* p : parts) delete p;
+}
+
+namespace {
+// the shard that holds local replicate i of a (possibly multi-device) result; i becomes the index inside it
+inline jsb_result* part_of(jsb_result* r, int64_t& i) {
+  if (r->parts.empty()) return r;
+  size_t k = (size_t)(std::upper_bound(r->part_off.begin(), r->part_off.end(), i) - r->part_off.begin()) - 1;
+  i -= r->part_off[k];
+  return r->parts[k];
+}
+inline const jsb_result* part_of(const jsb_result* r, int64_t& i) { return part_of(const_cast<jsb_result*>(r), i); }
+}  // namespace
 
 namespace jsb {
 
@@ -460,33 +482,70 @@ int validate_params(const jsb_graph* g, const jsb_params& p, int64_t idx) {
   return JSB_OK;
 }
 
-int upload_graph(jsb_graph* g, int device) {
+// The copy of the graph on `device` (the current device), created / refreshed under the graph's lock.
+int upload_graph(jsb_graph* g, int device, jsb_graph::DevCopy* out) {
   int rc = JSB_OK;
-  if (g->dev != device) {
-    g->drop_device();
-    g->dev = device;
-    if (g->kind == 1) {
-      CUDA_TRY(cudaMalloc(&g->d_rowptr, sizeof(uint32_t) * g->rowptr.size()));
-      CUDA_TRY(cudaMalloc(&g->d_colidx, sizeof(uint32_t) * std::max<size_t>(1, g->colidx.size())));
-      CUDA_TRY(cudaMemcpy(g->d_rowptr, g->rowptr.data(), sizeof(uint32_t) * g->rowptr.size(), cudaMemcpyHostToDevice));
-      CUDA_TRY(cudaMemcpy(g->d_colidx, g->colidx.data(), sizeof(uint32_t) * g->colidx.size(), cudaMemcpyHostToDevice));
-    }
+  std::lock_guard<std::mutex> lk(g->mu);
+  jsb_graph::DevCopy& d = g->dev[device];
+  if (g->kind == 1 && !d.d_rowptr) {
+    CUDA_TRY(cudaMalloc(&d.d_rowptr, sizeof(uint32_t) * g->rowptr.size()));
+    CUDA_TRY(cudaMalloc(&d.d_colidx, sizeof(uint32_t) * std::max<size_t>(1, g->colidx.size())));
+    CUDA_TRY(cudaMemcpy(d.d_rowptr, g->rowptr.data(), sizeof(uint32_t) * g->rowptr.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.d_colidx, g->colidx.data(), sizeof(uint32_t) * g->colidx.size(), cudaMemcpyHostToDevice));
   }
-  if (!g->d_cand_valid) {
-    cudaFree(g->d_cand);
-    g->d_cand = nullptr;
+  if (d.cand_version != g->cand_version) {
+    cudaFree(d.d_cand);
+    d.d_cand = nullptr;
     std::vector<uint32_t> c0(g->cand.size());
     for (size_t i = 0; i < c0.size(); ++i) c0[i] = (uint32_t)(g->cand[i] - 1);
-    CUDA_TRY(cudaMalloc(&g->d_cand, sizeof(uint32_t) * std::max<size_t>(1, c0.size())));
-    CUDA_TRY(cudaMemcpy(g->d_cand, c0.data(), sizeof(uint32_t) * c0.size(), cudaMemcpyHostToDevice));
-    g->d_ncand = (uint32_t)c0.size();
-    g->d_cand_valid = true;
+    CUDA_TRY(cudaMalloc(&d.d_cand, sizeof(uint32_t) * std::max<size_t>(1, c0.size())));
+    CUDA_TRY(cudaMemcpy(d.d_cand, c0.data(), sizeof(uint32_t) * c0.size(), cudaMemcpyHostToDevice));
+    d.d_ncand = (uint32_t)c0.size();
+    d.cand_version = g->cand_version;
   }
+  *out = d;
 done:
   return rc;
 }
 
+// Per-device state: one lock that serialises jsb_run on a device (launch configuration of the kernels and the
+// cached buffers below are per device), and the large device buffers kept between calls.
+enum { BUF_WS, BUF_LOG, BUF_CHUNK_OWNER, BUF_CHUNK_SEQ, BUF_GATHER, BUF_OUT_CLONE, BUF_OUT_CELL, BUF_OUT_LISTS, BUF_CLONES, BUF_N };
+struct DeviceState {
+  std::mutex mu;
+  struct Buf { void* p = nullptr; size_t bytes = 0; } buf[BUF_N];
+};
+DeviceState g_devs[64];
+
+// a cached device buffer of at least `bytes` (grown with 1/8 headroom); nullptr + *err on failure
+void* dev_buf(DeviceState& ds, int slot, size_t bytes, cudaError_t* err) {
+  DeviceState::Buf& b = ds.buf[slot];
+  *err = cudaSuccess;
+  if (b.p && b.bytes >= bytes) return b.p;
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+  size_t want = bytes + bytes / 8;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) { cudaGetLastError(); want = bytes; e = cudaMalloc(&b.p, want); }
+  if (e != cudaSuccess) { cudaGetLastError(); b.p = nullptr; *err = e; return nullptr; }
+  b.bytes = want;
+  return b.p;
+}
+#define DEV_BUF(ptr, type, slot, bytes)                                                       \
+  do {                                                                                        \
+    cudaError_t _e;                                                                           \
+    ptr = (type)dev_buf(ds, slot, (bytes), &_e);                                              \
+    if (!ptr) {                                                                               \
+      rc = fail(_e == cudaErrorMemoryAllocation ? JSB_ENOMEM : JSB_ECUDA, "device allocation of %zu bytes failed: %s", (size_t)(bytes), cudaGetErrorString(_e)); \
+      goto done;                                                                              \
+    }                                                                                         \
+  } while (0)
+
 }  // namespace
+
+namespace {
+int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t reps_per_point, const jsb_run_opts* opts,
+               int device, int64_t g_begin, int64_t g_end, jsb_result** out);
+}
 
 extern "C" {
 
@@ -516,13 +575,101 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
   }
   int ndev = jsb_device_count();
   if (ndev <= 0) return fail(JSB_ENODEVICE, "no CUDA device available; libjspace_b200 has no CPU fallback");
-  if (opts->device < 0 || opts->device >= ndev) return fail(JSB_EINVAL, "device %d is outside 0..%d", opts->device, ndev - 1);
-  if (need_closeness && !g->have_cand) {
-    const int64_t* s;
-    int64_t n;
-    jsb_graph_seed_candidates(g, &s, &n);
+  std::vector<int> devs;
+  if (opts->n_devices > 0) {
+    if (!opts->devices) return fail(JSB_EINVAL, "opts.devices is null");
+    for (int k = 0; k < opts->n_devices; ++k) {
+      const int d = opts->devices[k];
+      if (d < 0 || d >= ndev || d >= 64) return fail(JSB_EINVAL, "device %d is outside 0..%d", d, ndev - 1);
+      if (std::find(devs.begin(), devs.end(), d) != devs.end()) return fail(JSB_EINVAL, "device %d is listed twice", d);
+      devs.push_back(d);
+    }
+  } else {
+    if (opts->device < 0 || opts->device >= ndev || opts->device >= 64) return fail(JSB_EINVAL, "device %d is outside 0..%d", opts->device, ndev - 1);
+    devs.push_back(opts->device);
   }
+  if (need_closeness) {
+    // exact closeness centrality is one BFS per vertex on the host, O(V*E): seconds for 10^4 vertices, hours for
+    // 10^6.  Large graphs must come with their seed candidates (jsb_graph_set_seed_candidates).
+    std::unique_lock<std::mutex> lk(g->mu);
+    if (!g->have_cand) {
+      if (g->nv > 50000) return fail(JSB_EINVAL, "graph has %lld vertices and no seed candidates: the closeness arg-max of src/J_Space.jl:83-85 is O(V*E) on the host; call jsb_graph_set_seed_candidates (or jsb_graph_seed_candidates once, to compute and cache it)", (long long)g->nv);
+      lk.unlock();
+      const int64_t* sv;
+      int64_t sn;
+      jsb_graph_seed_candidates(g, &sv, &sn);
+    }
+  }
+  if (devs.size() == 1 || g_end - g_begin < 2) return run_single(g, points, n_points, reps_per_point, opts, devs[0], g_begin, g_end, out);
 
+  // ---- several devices: contiguous shards, one host thread per device ----------------------------------
+  const int nd = (int)std::min<int64_t>((int64_t)devs.size(), g_end - g_begin);
+  std::vector<jsb_result*> parts((size_t)nd, nullptr);
+  std::vector<int> rcs((size_t)nd, JSB_OK);
+  std::vector<std::string> errs((size_t)nd);
+  std::vector<int64_t> cut((size_t)nd + 1);
+  const int64_t total = g_end - g_begin, base = total / nd, extra = total % nd;
+  cut[0] = g_begin;
+  for (int k = 0; k < nd; ++k) cut[k + 1] = cut[k] + base + (k < extra ? 1 : 0);
+  {
+    std::vector<std::thread> th;
+    for (int k = 0; k < nd; ++k)
+      th.emplace_back([&, k]() {
+        rcs[k] = run_single(g, points, n_points, reps_per_point, opts, devs[k], cut[k], cut[k + 1], &parts[k]);
+        if (rcs[k] != JSB_OK) errs[k] = g_err;  // g_err is thread-local
+      });
+    for (auto& t : th) t.join();
+  }
+  for (int k = 0; k < nd; ++k)
+    if (rcs[k] != JSB_OK) {
+      for (jsb_result* p : parts) delete p;
+      return fail(rcs[k], "device %d: %s", devs[k], errs[k].c_str());
+    }
+  jsb_result* res = new (std::nothrow) jsb_result();
+  if (!res) { for (jsb_result* p : parts) delete p; return fail(JSB_ENOMEM, "out of host memory"); }
+  res->n_local = total; res->n_points = n_points; res->reps_per_point = reps_per_point; res->g_begin = g_begin;
+  res->nv = (uint32_t)g->nv; res->flags = opts->flags;
+  for (int k = 0; k < nd; ++k) {
+    res->part_off.push_back(cut[k] - g_begin);
+    res->summaries.insert(res->summaries.end(), parts[k]->summaries.begin(), parts[k]->summaries.end());
+    res->kernel_ms = std::max(res->kernel_ms, parts[k]->kernel_ms);  // the devices ran side by side
+    res->launches += parts[k]->launches;
+    res->max_snap = std::max(res->max_snap, parts[k]->max_snap);
+  }
+  res->parts = parts;
+  *out = res;
+  return JSB_OK;
+}
+
+void jsb_trim(void) {
+  int cur = 0;
+  cudaGetDevice(&cur);
+  const int ndev = jsb_device_count();
+  for (int d = 0; d < ndev && d < 64; ++d) {
+    std::lock_guard<std::mutex> lk(g_devs[d].mu);
+    bool any = false;
+    for (auto& b : g_devs[d].buf) any = any || b.p;
+    if (!any) continue;
+    cudaSetDevice(d);
+    for (auto& b : g_devs[d].buf) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+  }
+  cudaSetDevice(cur);
+  void* drop = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    drop = g_pin_ptr; g_pin_ptr = nullptr; g_pin_bytes = 0;
+  }
+  if (drop) cudaFreeHost(drop);
+}
+
+}  // extern "C"
+
+namespace {
+
+int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t reps_per_point, const jsb_run_opts* opts,
+               const int device, const int64_t g_begin, const int64_t g_end, jsb_result** out) {
+  using namespace jsb;
+  *out = nullptr;
   const int64_t n_local = g_end - g_begin;
   int rc = JSB_OK;
   PhaseTimer pt;
@@ -561,15 +708,22 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
   cudaStream_t stream = nullptr;
   int prev_dev = 0;
   cudaGetDevice(&prev_dev);
+  jsb_graph::DevCopy gd;
+  DeviceState& ds = g_devs[device];
 
   if (n_local == 0) { *out = res; return JSB_OK; }
 
+  std::unique_lock<std::mutex> dev_lock(ds.mu);  // one jsb_run at a time per device
   {
-    CUDA_TRY(cudaSetDevice(opts->device));
-    rc = upload_graph(g, opts->device);
+    CUDA_TRY(cudaSetDevice(device));
+    rc = upload_graph(g, device, &gd);
     if (rc != JSB_OK) goto done;
     CUDA_TRY(cudaStreamCreate(&stream));
-    CUDA_TRY(cudaDeviceSetLimit(cudaLimitStackSize, 8192));
+    {  // the kernels need 8 KB of stack per thread; never lower what the host application has set
+      size_t cur_stack = 0;
+      CUDA_TRY(cudaDeviceGetLimit(&cur_stack, cudaLimitStackSize));
+      if (cur_stack < 8192) CUDA_TRY(cudaDeviceSetLimit(cudaLimitStackSize, 8192));
+    }
 
     // ---- sweep points ---------------------------------------------------------------------
     std::vector<DevPoint> hp((size_t)n_points);
@@ -611,7 +765,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
 
     // ---- launch geometry ------------------------------------------------------------------
     cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, opts->device));
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     RunArgs a;
     std::memset(&a, 0, sizeof a);
     a.g.nv = (uint32_t)g->nv;
@@ -684,14 +838,14 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
     }
     const uint32_t site_bytes = a.site_bytes;
     const WsLayout L = ws_layout((uint32_t)g->nv, arena_cap, site_bytes);
-    CUDA_TRY(cudaMalloc(&d_ws, L.total * slots));
+    DEV_BUF(d_ws, uint8_t*, BUF_WS, L.total * slots);
 
     // ---- outputs --------------------------------------------------------------------------
     CUDA_TRY(cudaMalloc(&d_sum, sizeof(jsb_summary) * n_local));
     CUDA_TRY(cudaMalloc(&d_counters, sizeof(unsigned long long) * 3));
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 3, stream));
     unsigned long long clone_cap = std::min<unsigned long long>((unsigned long long)n_local * kMaxClones, 8ull << 20);
-    CUDA_TRY(cudaMalloc(&d_clones, sizeof(jsb_clone) * clone_cap));
+    DEV_BUF(d_clones, jsb_clone*, BUF_CLONES, sizeof(jsb_clone) * clone_cap);
     CUDA_TRY(cudaMalloc(&d_clone_off, sizeof(long long) * n_local));
     uint32_t n_chunks = 0;
     if (opts->flags & JSB_OUT_EVENTS) {
@@ -700,24 +854,24 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
       uint64_t want = opts->log_pool_bytes ? opts->log_pool_bytes : (1ull << 30);
       want = std::min<uint64_t>(want, free_b / 3);
       n_chunks = (uint32_t)std::max<uint64_t>(1, want / (sizeof(jsb_event) * kLogChunk));
-      CUDA_TRY(cudaMalloc(&d_log, sizeof(jsb_event) * kLogChunk * (size_t)n_chunks));
+      DEV_BUF(d_log, jsb_event*, BUF_LOG, sizeof(jsb_event) * kLogChunk * (size_t)n_chunks);
       CUDA_TRY(cudaMalloc(&d_chunk_next, sizeof(uint32_t)));
       CUDA_TRY(cudaMemsetAsync(d_chunk_next, 0, sizeof(uint32_t), stream));
-      CUDA_TRY(cudaMalloc(&d_chunk_owner, sizeof(int32_t) * n_chunks));
-      CUDA_TRY(cudaMalloc(&d_chunk_seq, sizeof(uint32_t) * n_chunks));
+      DEV_BUF(d_chunk_owner, int32_t*, BUF_CHUNK_OWNER, sizeof(int32_t) * n_chunks);
+      DEV_BUF(d_chunk_seq, uint32_t*, BUF_CHUNK_SEQ, sizeof(uint32_t) * n_chunks);
     }
     if (max_snap > 0) {
       CUDA_TRY(cudaMalloc(&d_snaps, sizeof(jsb_snapshot) * (size_t)max_snap * n_local));
       CUDA_TRY(cudaMemsetAsync(d_snaps, 0xFF, sizeof(jsb_snapshot) * (size_t)max_snap * n_local, stream));
     }
     if (opts->flags & JSB_OUT_LATTICE) {
-      CUDA_TRY(cudaMalloc(&d_out_clone, sizeof(uint16_t) * (size_t)g->nv * n_local));
-      CUDA_TRY(cudaMalloc(&d_out_cell, sizeof(uint32_t) * (size_t)g->nv * n_local));
+      DEV_BUF(d_out_clone, uint16_t*, BUF_OUT_CLONE, sizeof(uint16_t) * (size_t)g->nv * n_local);
+      DEV_BUF(d_out_cell, uint32_t*, BUF_OUT_CELL, sizeof(uint32_t) * (size_t)g->nv * n_local);
     }
-    if (opts->flags & JSB_OUT_LISTS) CUDA_TRY(cudaMalloc(&d_out_lists, sizeof(uint32_t) * 2 * (size_t)g->nv * n_local));
+    if (opts->flags & JSB_OUT_LISTS) DEV_BUF(d_out_lists, uint32_t*, BUF_OUT_LISTS, sizeof(uint32_t) * 2 * (size_t)g->nv * n_local);
 
     a.g.kind = g->kind; a.g.n1 = g->n1; a.g.n2 = g->n2; a.g.n3 = g->n3; a.g.nv = (uint32_t)g->nv;
-    a.g.rowptr = g->d_rowptr; a.g.colidx = g->d_colidx;
+    a.g.rowptr = gd.d_rowptr; a.g.colidx = gd.d_colidx;
     if (g->kind == 0) {
       // magic = ceil(2^(28+L) / d), L = ceil(log2 d): (v * magic) >> (28+L) == v / d for every v < 2^28
       auto magic = [](uint32_t d, uint32_t& m, uint32_t& sh) {
@@ -730,7 +884,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
       magic(g->n2, a.g.m2, a.g.s2);
     }
     a.points = d_points; a.dpool = d_dpool; a.ipool = d_ipool;
-    a.seed_cand = g->d_cand; a.n_cand = g->d_ncand;
+    a.seed_cand = gd.d_cand; a.n_cand = gd.d_ncand;
     a.flags = opts->flags; a.seed = opts->seed; a.g_begin = g_begin; a.n_local = n_local; a.reps_per_point = reps_per_point;
     a.ws = d_ws; a.ws_stride = L.total; a.arena_cap = arena_cap; a.site_bytes = site_bytes; a.L = L;
     a.summaries = d_sum; a.clone_pool = d_clones; a.clone_pool_cap = clone_cap; a.clone_pool_next = d_counters + 1;
@@ -849,7 +1003,7 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
         res->lists = (uint32_t*)(base + b_ev + b_lc + b_li);
       }
       if (ev_total > 0) {
-        CUDA_TRY(cudaMalloc(&d_gather, sizeof(jsb_event) * ev_total));
+        DEV_BUF(d_gather, jsb_event*, BUF_GATHER, sizeof(jsb_event) * ev_total);
         CUDA_TRY(cudaMalloc(&d_ev_off, sizeof(unsigned long long) * (n_local + 1)));
         CUDA_TRY(cudaMemcpyAsync(d_ev_off, res->ev_off.data(), sizeof(unsigned long long) * (n_local + 1), cudaMemcpyHostToDevice, stream));
         int gblocks = (int)std::min<uint32_t>(ev_used_chunks, (uint32_t)prop.multiProcessorCount * 8);
@@ -881,10 +1035,10 @@ int jsb_run(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t re
   }
 
 done:
-  cudaFree(d_points); cudaFree(d_dpool); cudaFree(d_ipool); cudaFree(d_ws); cudaFree(d_sum); cudaFree(d_clones);
-  cudaFree(d_counters); cudaFree(d_clone_off); cudaFree(d_log); cudaFree(d_gather); cudaFree(d_chunk_next);
-  cudaFree(d_chunk_owner); cudaFree(d_chunk_seq); cudaFree(d_ev_off); cudaFree(d_snaps); cudaFree(d_out_clone);
-  cudaFree(d_out_cell); cudaFree(d_out_lists); cudaFree(d_order); cudaFree(d_prio); cudaFree(d_trace);
+  // (d_ws, d_log, the chunk tables, d_gather, the lattice / list outputs and d_clones belong to the device cache)
+  cudaFree(d_points); cudaFree(d_dpool); cudaFree(d_ipool); cudaFree(d_sum);
+  cudaFree(d_counters); cudaFree(d_clone_off); cudaFree(d_chunk_next);
+  cudaFree(d_ev_off); cudaFree(d_snaps); cudaFree(d_order); cudaFree(d_prio); cudaFree(d_trace);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (stream) cudaStreamDestroy(stream);
@@ -894,6 +1048,10 @@ done:
   *out = res;
   return JSB_OK;
 }
+
+}  // namespace
+
+extern "C" {
 
 int jsb_result_kernel_ms(const jsb_result* r, double* elapsed_ms) {
   if (!r || !elapsed_ms) return fail(JSB_EINVAL, "null argument");
@@ -922,6 +1080,7 @@ int jsb_result_summaries(const jsb_result* r, const jsb_summary** p) {
 int jsb_result_clones(const jsb_result* r, int64_t i, const jsb_clone** p, int32_t* n) {
   CHECK_INDEX(r, i);
   if (!p || !n) return fail(JSB_EINVAL, "null argument");
+  r = part_of(r, i);
   long long off = r->clone_off[i];
   if (off < 0) return fail(JSB_ECAPACITY, "clone pool overflowed; replicate %lld has no clone table", (long long)i);
   *p = r->clones.data() + off;
@@ -933,6 +1092,7 @@ int jsb_result_events(jsb_result* r, int64_t i, const jsb_event** p, int64_t* n)
   CHECK_INDEX(r, i);
   if (!p || !n) return fail(JSB_EINVAL, "null argument");
   if (!(r->flags & JSB_OUT_EVENTS)) return fail(JSB_EINVAL, "run did not request JSB_OUT_EVENTS");
+  r = part_of(r, i);
   *p = r->events ? r->events + r->ev_off[i] : nullptr;
   *n = (int64_t)(r->ev_off[i + 1] - r->ev_off[i]);
   return JSB_OK;
@@ -941,6 +1101,7 @@ int jsb_result_events(jsb_result* r, int64_t i, const jsb_event** p, int64_t* n)
 int jsb_result_lattice(const jsb_result* r, int64_t i, const uint16_t** clone, const uint32_t** cell_id) {
   CHECK_INDEX(r, i);
   if (!(r->flags & JSB_OUT_LATTICE)) return fail(JSB_EINVAL, "run did not request JSB_OUT_LATTICE");
+  r = part_of(r, i);
   if (clone) *clone = r->lat_clone + (size_t)i * r->nv;
   if (cell_id) *cell_id = r->lat_cell + (size_t)i * r->nv;
   return JSB_OK;
@@ -950,6 +1111,7 @@ int jsb_result_list(jsb_result* r, int64_t i, int32_t list, const uint32_t** p, 
   CHECK_INDEX(r, i);
   if (!p || !n) return fail(JSB_EINVAL, "null argument");
   if (!(r->flags & JSB_OUT_LISTS)) return fail(JSB_EINVAL, "run did not request JSB_OUT_LISTS");
+  r = part_of(r, i);
   const jsb_summary& s = r->summaries[i];
   if (list < 0 || list > (int32_t)s.n_clones) return fail(JSB_EINVAL, "list %d is outside 0..n_clones", list);
   const uint32_t* base = r->lists + (size_t)i * 2 * r->nv;
@@ -968,6 +1130,7 @@ int jsb_result_list(jsb_result* r, int64_t i, int32_t list, const uint32_t** p, 
 int jsb_result_snapshots(const jsb_result* r, int64_t i, const jsb_snapshot** p, int32_t* n) {
   CHECK_INDEX(r, i);
   if (!p || !n) return fail(JSB_EINVAL, "null argument");
+  r = part_of(r, i);
   if (r->max_snap == 0) { *p = nullptr; *n = 0; return JSB_OK; }
   *p = r->snaps.data() + (size_t)i * r->max_snap;
   *n = r->snap_count[i];
@@ -1003,6 +1166,7 @@ int jsb_result_genealogy(jsb_result* r, int64_t i, const uint32_t* sample_cells,
   CHECK_INDEX(r, i);
   if (!rows || !n_rows || (n_samples > 0 && !sample_cells)) return fail(JSB_EINVAL, "null argument");
   if (!(r->flags & JSB_OUT_EVENTS)) return fail(JSB_EINVAL, "run did not request JSB_OUT_EVENTS");
+  r = part_of(r, i);
   const jsb_event* ev = r->events ? r->events + r->ev_off[i] : nullptr;
   const int64_t n = (int64_t)(r->ev_off[i + 1] - r->ev_off[i]);
   // every cell id appears as `cell` in at most one Duplicate/Mutation row (ids are unique), so
