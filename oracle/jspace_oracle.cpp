@@ -936,6 +936,23 @@ void orc_mt_raw(uint64_t mt_seed, uint64_t* out, int64_t n) {
   jmt::MersenneTwister m(mt_seed, v);
   for (int64_t k = 0; k + 1 < n; k += 2) m.ds.next(out + k);
 }
+// pinning aid: out[k] = the value randn() returns when its first raw double is dSFMT output k of
+// MersenneTwister(seed) and the ziggurat accepts at once (NaN otherwise: 1.2 % of the calls)
+void orc_mt_randn_scan(uint64_t mt_seed, int64_t n, double* out) {
+  jmt::Variant v;
+  jmt::MersenneTwister m(mt_seed, v);
+  const jmt::Zig& z = jmt::MersenneTwister::zig();
+  uint64_t w[2];
+  for (int64_t k = 0; k + 1 < n; k += 2) {
+    m.ds.next(w);
+    for (int h = 0; h < 2; ++h) {
+      const uint64_t r = w[h] & 0x000fffffffffffffULL;
+      const int64_t rabs = (int64_t)(r >> 1);
+      const unsigned idx = (unsigned)(rabs & 0xFF);
+      out[k + h] = (uint64_t)rabs < z.ki[idx] ? (double)((r & 1) ? -rabs : rabs) * z.wi[idx] : std::nan("");
+    }
+  }
+}
 int64_t orc_mt_randn_pos(void* s, const int64_t** p) {
   Sim* S = (Sim*)s;
   *p = S->mt_randn_pos.data();

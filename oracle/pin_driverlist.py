@@ -9,7 +9,15 @@ compares set_mut / alpha with the one output of this path the reference ships: f
 
     python oracle/pin_driverlist.py [path/to/DriverList.csv] [--search]
 
---search tries the alternatives of julia_mt.hpp's Variant knobs and reports which reproduce the file."""
+--search tries the alternatives of julia_mt.hpp's Variant knobs and reports which reproduce the file.
+
+Status (round 2): the generator, the Float64 conversion, the ziggurat normal (fast path, wedge rejection) and the
+fitness arithmetic ARE pinned against this file — tests/test_reference_pin.py finds all 73 fitness values bit for
+bit in the stream of MersenneTwister(1234), in row order, each right after a driver-test draw <= 0.01.  The
+whole-trajectory reproduction this script attempts is NOT achieved: the shipped file was not produced from the
+shipped Parameters.toml (its sibling formatNewick holds 100 sampled cells, Parameters.toml asks for 10; the
+neighbour draws before the 73 mutations use two random bits, i.e. a 2-D lattice, Parameters.toml says dim = 3),
+and the lattice size / death / migration rates / excision schedule of that run cannot be read off the file."""
 import ast
 import csv
 import ctypes as C
