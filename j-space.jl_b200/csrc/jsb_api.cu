@@ -814,12 +814,9 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
       }
       if (!fast_mode) {
         a.dec_min_clones = kDecMinClones;
-        a.defer_min_clones = kDeferMinClones;
         if (const char* e = std::getenv("JSB_DEC_MIN_CLONES")) a.dec_min_clones = (uint32_t)std::max(1, std::atoi(e));  // tuning hook
-        if (const char* e = std::getenv("JSB_DEFER_MIN_CLONES")) a.defer_min_clones = (uint32_t)std::max(1, std::atoi(e));  // tuning hook
         // Self-served deferred batches (no idle warp to serve them): measured slower than the exact fold in the
         // throughput phase of C2, so opt-in; batches are always handed to a server warp when one is attached.
-        a.defer = (std::getenv("JSB_DEFER") && !std::getenv("JSB_NO_CLOCK")) ? 1u : 0u;
       }
     }
     if (const char* e = std::getenv("JSB_DEBUG_GRID")) {  // debug: pack the replicates on fewer SMs (contention measurements)

@@ -15,8 +15,7 @@ constexpr int kMinListCap = 32;    // initial capacity of a ca_subpop list in th
 #ifndef JSB_MAXWARPS
 #define JSB_MAXWARPS 12
 #endif
-constexpr uint32_t kDecMinClones = 64;  // decoupled mode (clock helper): below this many clones the exact fold is cheaper than the hand-off (measured)
-constexpr uint32_t kDeferMinClones = 160;  // deferred mode (self-served batches): below this many clones the exact fold is cheaper
+constexpr uint32_t kDecMinClones = 64;  // decoupled mode: below this many clones the exact fold is cheaper than the hand-off (measured)
 constexpr int kMaxLook = 4;  // lookahead depth: helper warps evaluating later windows for one busy warp
 constexpr int kMaxHelp = kMaxLook + 1;  // plus the clock helper (exact fold and time chain off the critical path)
 constexpr int kMaxWarpsPerBlock = JSB_MAXWARPS;  // one block per SM; warps per block chosen at launch
@@ -98,9 +97,7 @@ struct RunArgs {
   unsigned long long* work_counter;
   uint32_t fast_smem_tree;  // rejection-free mode: upper tree levels live in shared memory
   uint32_t helpers;         // exact mode: idle warps of a block evaluate the next window for busy ones
-  uint32_t dec_min_clones;  // deferred mode only for replicates with at least this many clones
-  uint32_t defer_min_clones; // deferred mode (self-served batches) from this many clones on
-  uint32_t defer;           // exact mode: the exact fold / clock may be deferred and served in batches of 32 events
+  uint32_t dec_min_clones;  // decoupled mode only for replicates with at least this many clones
   uint32_t clock_max_busy;  // a clock helper is attached only while at most this many replicates run on the SM
   uint32_t static_map;      // fewer replicates than warps: replicate idx is owned by block idx % grid
   // optional longest-first scheduling: a pilot pass runs every replicate for

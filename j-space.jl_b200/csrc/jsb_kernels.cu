@@ -53,19 +53,12 @@ enum { PH_REFOLD, PH_DRAWS, PH_CLASS, PH_EVAL, PH_TIME, PH_BIRTH, PH_DEATH, PH_M
 __device__ long long g_sub[8];  // sub-phase cycle totals of one profiled replicate (lane 0)
 #define SUB_T0() long long _s0 = clock64()
 #define SUB_ADD(k) do { long long _s1 = clock64(); if ((threadIdx.x & 31) == 0) g_sub[k] += _s1 - _s0; _s0 = _s1; } while (0)
-// deferred-mode phases (one profiled replicate at a time): cycles and counts, lane 0
-enum { DP_EVAL, DP_HELP, DP_COMMIT, DP_DEATH, DP_BIRTH, DP_MIGR, DP_BOOK, DP_APPROX, DP_SERVE, DP_SV_A, DP_SV_WALK, DP_SV_CHAIN, DP_RESYNC, DP_N };
-__device__ long long g_dp[DP_N], g_dpn[DP_N];
-#define DP_T0() long long _d0 = clock64()
-#define DP_ADD(k) do { long long _d1 = clock64(); if ((threadIdx.x & 31) == 0) { g_dp[k] += _d1 - _d0; g_dpn[k]++; } _d0 = _d1; } while (0)
 #else
 #define PROF_DECL
 #define PROF_T0()
 #define PROF_ADD(ph)
 #define SUB_T0()
 #define SUB_ADD(k)
-#define DP_T0()
-#define DP_ADD(k)
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -567,69 +560,47 @@ __device__ __forceinline__ void a_append(const Ctx<T>& X, uint32_t n, uint32_t s
 
 // remove logical element p of n, keep order (whole warp).  `hint` (may be null): per-vertex segment numbers,
 // kept up to date for the one element per later segment that changes segment.
-// Latency is what matters here (one warp, dependent global-memory round trips): every load of the
-// in-segment shift and of the first 128 later segments is issued before the first store — head[s], then
-// {in-segment elements, later heads}, then the later segments' fronts: three round trips per delete.
 template <typename T>
 __device__ __noinline__ void a_remove(T* A, uint16_t* head, uint32_t n, uint32_t p, int lane, T* hint) {
-  constexpr uint32_t K = 4;          // later segments per lane and pass
-  constexpr uint32_t R = kSeg / 32;  // in-segment elements per lane
   const uint32_t s = p / kSeg, i = p & (kSeg - 1u);
-  const uint32_t ls = (n - 1) / kSeg;  // last segment
+  const uint32_t ls = (n - 1) / kSeg;                       // last segment
   const uint32_t cnt = (s == ls) ? ((n - 1) & (kSeg - 1u)) + 1u : kSeg;
   const uint32_t hs = head[s];
   T* seg = A + s * kSeg;
   // inside segment s: logical j <- j+1 for j in [i, cnt-1)
-  T v[R];
-#pragma unroll
-  for (uint32_t k = 0; k < R; ++k) {
-    const uint32_t j = i + (uint32_t)lane + 32u * k;
-    v[k] = 0;
-    if (j + 1 < cnt) v[k] = seg[(hs + j + 1) & (kSeg - 1u)];
+  for (uint32_t base = i; base + 1 < cnt; base += 32) {
+    const uint32_t j = base + lane;
+    T v = 0;
+    const bool act = j + 1 < cnt;
+    if (act) v = seg[(hs + j + 1) & (kSeg - 1u)];
+    __syncwarp();
+    if (act) seg[(hs + j) & (kSeg - 1u)] = v;
+    __syncwarp();
   }
-  // every later segment t hands its front to the back of t-1 and rotates by one.  Back slot of t-1:
-  // segment s kept its head (slot head + kSeg - 1); a later one rotated, so its new back is its old front slot.
-  bool first_pass = true;
-  for (uint32_t base = s + 1; base <= ls || first_pass; base += 32u * K) {
-    uint32_t ht[K], hp[K];
-    T f[K];
-#pragma unroll
-    for (uint32_t k = 0; k < K; ++k) {
-      const uint32_t t = base + (uint32_t)lane + 32u * k;
-      ht[k] = hp[k] = 0;
-      if (t <= ls) {
-        ht[k] = head[t];
-        hp[k] = head[t - 1];
-        // the previous pass already advanced the head of its last segment
-        if (!first_pass && t == base) hp[k] = (hp[k] + kSeg - 1u) & (kSeg - 1u);
-      }
+  // every later segment hands its front to the back of its predecessor and rotates by one
+  uint32_t prev_head_carry = hs;  // head of segment t-1 before this call, for the first lane
+  for (uint32_t base = s + 1; base <= ls; base += 32) {
+    const uint32_t t = base + lane;
+    const bool act = t <= ls;
+    uint32_t ht = 0, hp = 0;
+    T v = 0;
+    if (act) {
+      ht = head[t];
+      hp = (lane == 0) ? prev_head_carry : (uint32_t)head[t - 1];
+      v = A[t * kSeg + ht];
     }
-#pragma unroll
-    for (uint32_t k = 0; k < K; ++k) {
-      const uint32_t t = base + (uint32_t)lane + 32u * k;
-      f[k] = 0;
-      if (t <= ls) f[k] = A[t * kSeg + ht[k]];
-    }
+    const uint32_t last_ht = __shfl_sync(FULL, ht, 31);
     __syncwarp();
-    if (first_pass) {
-#pragma unroll
-      for (uint32_t k = 0; k < R; ++k) {
-        const uint32_t j = i + (uint32_t)lane + 32u * k;
-        if (j + 1 < cnt) seg[(hs + j) & (kSeg - 1u)] = v[k];
-      }
+    if (act) {
+      // back slot of t-1: segment s kept its head (slot head+kSeg-1); later ones rotated, so their
+      // new back is their old front slot
+      const uint32_t slot = (t - 1 == s) ? ((hs + kSeg - 1u) & (kSeg - 1u)) : hp;
+      A[(t - 1) * kSeg + slot] = v;
+      head[t] = (uint16_t)((ht + 1u) & (kSeg - 1u));
+      if (hint) hint[v] = (T)(t - 1u);
     }
-#pragma unroll
-    for (uint32_t k = 0; k < K; ++k) {
-      const uint32_t t = base + (uint32_t)lane + 32u * k;
-      if (t <= ls) {
-        const uint32_t slot = (t - 1 == s) ? ((hs + kSeg - 1u) & (kSeg - 1u)) : hp[k];
-        A[(t - 1) * kSeg + slot] = f[k];
-        head[t] = (uint16_t)((ht[k] + 1u) & (kSeg - 1u));
-        if (hint) hint[f[k]] = (T)(t - 1u);
-      }
-    }
+    prev_head_carry = last_ht;
     __syncwarp();
-    first_pass = false;
   }
 }
 
@@ -1820,18 +1791,27 @@ struct HelpRes {
   double dt[32];
   double sum_dt, pad2;  // dt[0] + ... + dt[first state-changing lane] (all 32 when there is none), any order
 };
-// Channel to the batch server of a replicate: an idle warp of the block that runs deferred_serve (the exact
-// folds and the exact clock of 32 events at a time) while the owner goes on with the next batch.
+// Channel to the "clock" helper of a replicate (decoupled mode, see clock_serve).
 struct ClockChan {
-  uint32_t attached, warp;    // a server is attached; its warp slot (its shared slice receives the batches)
-  uint32_t posted, done;      // batches handed over by the owner / finished by the server
-  uint32_t claimed;           // an idle warp has taken the role (attached follows once it is ready)
-  uint32_t ne, tail_m, S;     // posted batch: events, iterations after the last event, clones at its end
-  uint32_t ring_off, init;    // where its unit exponentials start in the ring; 1: start from t_init / lam_init
-  uint32_t pad[2];
-  double t_exact, lam_exact;  // exact clock and total rate after batch `done`
-  double t_init, lam_init;
+  uint32_t attached, warp;   // a clock helper serves this replicate; its warp slot (its shared slice holds the ring)
+  uint32_t posted, done;     // sequence numbers: last message written by the owner / finished by the helper
+  uint32_t claimed, pad[3];  // an idle warp has taken the clock role (attached follows once it is ready)
+  double t_exact, lambda_exact;  // exact time and total rate after message `done`
+  double t_init, lambda_init;    // payload of an INIT message
 };
+struct ClockMsg {
+  unsigned long long it_first;  // the round committed iterations it_first+1 .. it_first+m
+  uint32_t kind, m;             // 0 INIT, 1 ROUND
+  uint32_t from, S, n;          // state after the round's event: fold from clone `from` (kNone: unchanged)
+  uint32_t n_rows, n_upd, pad;
+  uint32_t rows[3];             // log records of the event (chunk * kLogChunk + slot): their time is the round's end
+  uint32_t upd_idx[3];          // clones whose size changed ...
+  int32_t upd_kind[3];          // ... by +1 / -1, or 2 = new clone of size 1
+  uint32_t pad2;
+};
+static_assert(sizeof(ClockMsg) == 80, "ring slots are 16-byte multiples");
+constexpr uint32_t kClockRing = 8;
+constexpr uint32_t kClockResync = 1024;  // events between two exact re-bases of the owner's approximate table
 struct HelpMail {
   uint32_t word;          // (request id << 8) | helpers asked; written last by the owner
   uint32_t nhelp, done;   // helpers attached (only grows); the owner has no work left
@@ -1899,34 +1879,167 @@ __device__ __noinline__ void helper_serve(Ctx<T> X, volatile HelpMail* M, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// The shared slice of another warp of the block (the batch server works in its own slice, see "Deferred mode").
+// Decoupled mode: the clock helper.
+//
+// Two sequential fp64 chains sit on a replicate's critical path after every event: the fold that
+// gives the exact total rate λ (`sum`, :692-698) and the time chain t += e·(1/λ) (:699-701).
+// Neither decides what happens next, except near Tf / an excision time / a snapshot time: the
+// event class is decided by comparing k·λ with the class boundaries, and that decision is the
+// same for any boundaries within the guard band of the exact ones (§4 of DESIGN.md; inside the
+// band the exact prob_cum table decides).  So when an idle warp is available the owner keeps an
+// APPROXIMATE table (each event's ±α added to the suffix in parallel, re-based on the exact one
+// every kClockResync events) and an approximate clock, and streams what it did to the clock helper,
+// which owns the exact table, replays the exact fold and time chain one round behind, and patches
+// the exact event times into the log records.  Whenever the approximate clock comes within a
+// relative 1e-9 of a time that matters, or a draw lands in the guard band, the owner waits for
+// the helper, takes over its exact state and runs that round on the exact path.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned char* slice_of(const double* my_B, int my_warp, uint32_t smem_per_warp, uint32_t warp) {
   return reinterpret_cast<unsigned char*>(const_cast<double*>(my_B)) + ((long)warp - (long)my_warp) * (long)smem_per_warp;
 }
-// ---------------------------------------------------------------------------------------------
-// Deferred mode: the exact fold and the exact clock, 32 events at a time.
-//
-// Two sequential fp64 chains sit on a replicate's critical path after every event: the fold that
-// gives the exact total rate λ (`sum`, :692-698; S dependent adds) and the time chain t += e·(1/λ)
-// (:699-701).  Neither decides what happens next, except near Tf / an excision time / a snapshot
-// time: the event class is decided by comparing k·λ with the class boundaries, and that decision is
-// the same for any boundaries within the guard band of the exact ones (§4 of DESIGN.md; inside the
-// band the exact prob_cum table decides).  So the replicate runs on an APPROXIMATE table (each
-// event's ±α added to the suffix in parallel, re-based on the exact one every kApproxResync events)
-// and an approximate clock, and remembers what every event did.  After 32 events the exact values are
-// computed for all of them at once: lane e folds the clone sizes as they were after event e — 32
-// independent sequential chains run in lock step, so 32 exact folds cost one — then the exact time
-// chain is replayed over the committed iterations (their unit exponentials were kept) and the exact
-// event times are written into the log records.  Whenever the approximate clock comes within a
-// relative 1e-9 of a time that matters, a draw lands in the guard band, or the replicate ends, the
-// pending events are served and that round runs on the exact path.  Every value the reference
-// computes is still computed in the reference's order.
-// ---------------------------------------------------------------------------------------------
-constexpr uint32_t kApproxResync = 1024;  // events between two exact re-bases of the approximate table
+template <typename T>
+__device__ __forceinline__ volatile ClockMsg* ring_of(unsigned char* slice) {  // the helper's (idle) c_off8 region
+  static_assert(sizeof(T) * kTab >= sizeof(ClockMsg) * kClockRing, "the ring fits the region");
+  return reinterpret_cast<volatile ClockMsg*>(slice + sizeof(double) * (kSmemTable + 32) + sizeof(T) * kTab);
+}
+
+// XO: the owner's context; `mine`: this (idle) warp's own shared slice, reused as
+// [ exact B table | dt staging | exact c_len copy | message ring ].
+template <typename T>
+__device__ __noinline__ void clock_serve(Ctx<T> XO, volatile HelpMail* M, unsigned char* mine) {
+  const int lane = XO.lane;
+  const RunArgs& A = *XO.A;
+  volatile ClockChan* C = &M->clk;
+  volatile ClockMsg* ring = ring_of<T>(mine);
+  // the owner's context with the tables redirected to this warp's slice
+  Ctx<T> XF = XO;
+  XF.B = reinterpret_cast<double*>(mine);
+  XF.c_len = reinterpret_cast<T*>(mine + sizeof(double) * (kSmemTable + 32));
+  XF.sB = smem_addr(XF.B);
+  XF.sDt = XF.sB + 8u * kSmemTable;
+  XF.sLen = smem_addr(XF.c_len);
+  const uint32_t soB = XO.sB, soLen = XO.sLen;
+  double t = 0.0, lambda = 1.0, theta = 1.0;
+  uint32_t seq = C->done;
+  if (lane == 0) { C->warp = (uint32_t)(threadIdx.x >> 5); __threadfence_block(); C->attached = 1; }
+  __syncwarp();
+  for (;;) {
+    while (C->posted == seq) {
+      if (M->done) return;
+      __nanosleep(20);
+    }
+    __threadfence_block();
+    ++seq;
+    volatile ClockMsg* m = &ring[seq % kClockRing];
+    const uint32_t kind = m->kind, S = m->S, n = m->n;
+    if (kind == 0) {  // INIT: take over the owner's exact table, sizes, clock
+      for (uint32_t i = lane; i < S + 2; i += 32) sts_f64(XF.sB + i * 8u, lds_f64(soB + i * 8u));
+      for (uint32_t i = lane; i < S; i += 32) XF.c_len[i] = (T)lds_tab<T>(soLen, i);
+      t = C->t_init;
+      lambda = C->lambda_init;
+      theta = 1.0 / lambda;
+      __syncwarp();
+    } else {
+      // exact time chain over the committed iterations, with the rate of the state they ran in
+      const uint32_t cnt = m->m;
+      const uint64_t it0 = m->it_first;
+      XF.key.stream = M->stream;
+      for (uint32_t done = 0; done < cnt; done += 32) {
+        const uint32_t left = cnt - done;
+        const uint64_t q = it0 + 1 + done + (uint64_t)lane;
+        uint64_t wa, wb;
+        draw_block(XF.key, q, 0, DS_TIME_CLASS, 0, wa, wb);
+        const double dt = (-contract_log(u01_open(wa))) * theta;  // :699
+        t = time_chain(XF.sDt, lane, t, dt, left >= 32u ? 31u : left - 1u);  // :701
+      }
+      const uint32_t n_rows = m->n_rows;
+      if (lane < (int)n_rows) *reinterpret_cast<double*>(A.log_pool + m->rows[lane]) = t;
+      const uint32_t from = m->from;
+      if (from != kNone) {
+        const uint32_t n_upd = m->n_upd;
+        if (lane == 0) {
+          for (uint32_t u = 0; u < n_upd; ++u) {
+            const uint32_t idx = m->upd_idx[u];
+            const int k = m->upd_kind[u];
+            XF.c_len[idx] = (T)(k == 2 ? 1u : (uint32_t)XF.c_len[idx] + (uint32_t)k);
+          }
+        }
+        __syncwarp();
+        Rep rf;
+        rf.S = S; rf.n = n; rf.dirty_from = from; rf.lambda = lambda; rf.theta = theta; rf.guard = 0.0; rf.exact_valid = false;
+        refold(XF, rf);
+        lambda = rf.lambda;
+        theta = rf.theta;
+      }
+    }
+    if (lane == 0) {
+      C->t_exact = t;
+      C->lambda_exact = lambda;
+      __threadfence_block();
+      C->done = seq;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- owner side -----------------------------------------------------------------------------
+__device__ __forceinline__ void clock_wait_idle(volatile ClockChan* C) {
+  while (C->done != C->posted) __nanosleep(20);
+  __threadfence_block();
+}
+
+// writes one message into the helper's ring (lane 0), waiting for a free slot
+__device__ __noinline__ void clock_post(volatile HelpMail* M, volatile ClockMsg* ring, int lane, uint32_t kind,
+                                        unsigned long long it_first, uint32_t m, uint32_t from, uint32_t S, uint32_t n,
+                                        uint32_t n_rows, uint32_t row0, uint32_t row1, uint32_t row2, uint32_t n_upd,
+                                        uint32_t u0, int k0, uint32_t u1, int k1, uint32_t u2, int k2) {
+  volatile ClockChan* C = &M->clk;
+  uint32_t seq = 0;
+  if (lane == 0) {
+    seq = C->posted + 1u;
+    while (seq - C->done > kClockRing - 1u) __nanosleep(20);
+    volatile ClockMsg* q = &ring[seq % kClockRing];
+    q->it_first = it_first; q->kind = kind; q->m = m; q->from = from; q->S = S; q->n = n;
+    q->n_rows = n_rows; q->rows[0] = row0; q->rows[1] = row1; q->rows[2] = row2;
+    q->n_upd = n_upd; q->upd_idx[0] = u0; q->upd_idx[1] = u1; q->upd_idx[2] = u2;
+    q->upd_kind[0] = k0; q->upd_kind[1] = k1; q->upd_kind[2] = k2;
+    __threadfence_block();  // the event's stores (lists, fitness table, log records) and the message, before the count
+    C->posted = seq;
+  }
+  __syncwarp();
+}
+
+// Enter decoupled mode: the owner's table is exact and clean.
+template <typename T>
+__device__ __noinline__ void dec_enter(Ctx<T>& X, Rep& r, volatile HelpMail* M, volatile ClockMsg* ring) {
+  volatile ClockChan* C = &M->clk;
+  if (X.lane == 0) {
+    C->t_init = r.t; C->lambda_init = r.lambda; M->stream = X.key.stream;
+    atomicAdd(X.A->work_counter + 2, 1ull);  // statistics: entries into decoupled mode (JSB_TIMING)
+  }
+  __syncwarp();
+  clock_post(M, ring, X.lane, 0u, r.it, 0u, kNone, r.S, r.n, 0u, 0u, 0u, 0u, 0u, 0u, 0, 0u, 0, 0u, 0);
+  clock_wait_idle(C);
+}
+
+// Leave decoupled mode: wait for the helper, take its exact table, total rate and clock.
+template <typename T>
+__device__ __noinline__ void dec_leave(Ctx<T>& X, Rep& r, volatile HelpMail* M, unsigned char* helper_slice) {
+  volatile ClockChan* C = &M->clk;
+  clock_wait_idle(C);
+  const uint32_t sF = smem_addr(helper_slice);
+  for (uint32_t i = X.lane; i < r.S + 2; i += 32) sts_f64(X.sB + i * 8u, lds_f64(sF + i * 8u));
+  r.t = C->t_exact;
+  r.lambda = C->lambda_exact;
+  r.theta = 1.0 / r.lambda;  // :699, the same expression the fold uses
+  r.guard = ((X.P->quirks & JSB_QUIRK_DEBUG_WIDE_GUARD) ? 1e-3 : kGuardEps) * r.lambda;
+  r.exact_valid = false;
+  r.dirty_from = kNone;
+  __syncwarp();
+}
 
 // The approximate counterpart of refold(): every boundary from the changed clones on moves by the
-// same ±α (one rounding per entry per event; re-based on the exact table every kApproxResync events,
+// same ±α (one rounding per entry per event; re-based on the exact table every kClockResync events,
 // so the drift stays below 2e-13·λ, two orders of magnitude inside the guard band).
 template <typename T>
 __device__ __noinline__ void approx_update(Ctx<T>& X, Rep& r, uint32_t S_old, uint32_t i0, double a0, uint32_t i1, double a1,
@@ -1934,15 +2047,12 @@ __device__ __noinline__ void approx_update(Ctx<T>& X, Rep& r, uint32_t S_old, ui
   const uint32_t sB = X.sB;
   const uint32_t lo = i0 < i1 ? i0 : i1;
   if (lo != kNone) {
-    // plain loads and stores (the ordered asm accessors would serialise the iterations on the load latency)
-    double* __restrict__ Bt = X.B;
-#pragma unroll 4
     for (uint32_t i = lo + (uint32_t)X.lane; i < S_old; i += 32) {
-      double v = Bt[i];
+      double v = lds_f64(sB + i * 8u);
       if (i >= i0) v = v + a0;
       if (i >= i1) v = v + a1;
       // the class search orders the entries by their bit patterns: never negative (true values are >= 0)
-      Bt[i] = v < 0.0 ? 0.0 : v;
+      sts_f64(sB + i * 8u, v < 0.0 ? 0.0 : v);
     }
   }
   __syncwarp();
@@ -1969,285 +2079,42 @@ __device__ __noinline__ void approx_update(Ctx<T>& X, Rep& r, uint32_t S_old, ui
   __syncwarp();
 }
 
-// What one event of the current batch did; lane e holds event e.
-struct Pend {
-  uint32_t m;               // loop iterations committed since the previous event, this event's included
-  uint32_t S, n;            // clones / cells alive after the event
-  uint32_t n_rows, row[3];  // its log records (chunk * kLogChunk + slot): their time is the event's
-  uint32_t n_upd, ui[3];    // clones whose size changed ...
-  int32_t uk[3];            // ... by +1 / -1, or 2 = a new clone of size 1
-};
-
-// Serves the pending batch: exact λ after each of the `ne` events (lane-parallel folds), the exact time chain
-// over every committed iteration (`ring` holds their unit exponentials, in order), the log times.  `tail_m`
-// iterations after the last event are chained too.  lam_exact / t_exact: exact total rate and clock at the
-// start of the batch on entry, at its end on return.
+// ---------------------------------------------------------------------------------------------
+// One replicate
+// ---------------------------------------------------------------------------------------------
+// Runs rounds on the approximate clock (see clock_serve) until the exact state is needed again: a
+// time that matters comes within reach, a draw lands in the guard band, or the replicate ends.
+// On return the state is exact and clean (the helper's table, rate and clock have been taken
+// over); returns true when the replicate is over (extinction or an error status).
 template <typename T>
-__device__ __noinline__ void deferred_serve(Ctx<T>& X, const uint32_t S, const Pend& pe, uint32_t ne, uint32_t tail_m,
-                                            const double* ring, double& lam_exact, double& t_exact) {
-  const int lane = X.lane;
-  const DevPoint& P = *X.P;
-  double lam = 0.0;  // lane e: exact λ after event e
-  DP_T0();
-  if (ne) {
-    double* __restrict__ gw = X.g_w;  // S = clones at the end of the batch
-    // w_i = α_i·n_i with the sizes at the END of the batch (:693), zero-padded to a multiple of sixteen
-    const uint32_t S16 = (S + 15u) & ~15u;
-    for (uint32_t base = (uint32_t)lane; base < S16; base += 256u) {
-      double a[8];
-#pragma unroll
-      for (uint32_t k = 0; k < 8u; ++k) {
-        const uint32_t i = base + 32u * k;
-        a[k] = i < S ? ldg_keep_f64(X.c_alpha + i) : 0.0;
-      }
-#pragma unroll
-      for (uint32_t k = 0; k < 8u; ++k) {
-        const uint32_t i = base + 32u * k;
-        if (i < S16) gw[i] = i < S ? a[k] * (double)lds_tab<T>(X.sLen, i) : 0.0;
-      }
-    }
-    // bitmap of the clones some event of the batch touched (1024 bits in the dt staging area)
-    uint32_t* bm = reinterpret_cast<uint32_t*>(X.B + kSmemTable);
-    bm[lane] = 0;
-    __syncwarp();
-    if ((uint32_t)lane < ne)
-      for (uint32_t k = 0; k < pe.n_upd; ++k) atomicOr(&bm[pe.ui[k] >> 5], 1u << (pe.ui[k] & 31u));
-    __syncwarp();
-    DP_ADD(DP_SV_A);
-    // lane e's own left fold over the sizes as they were after event e: n_i(e) = n_i(end) - (what the later
-    // events of the batch did to clone i); a clone born later has size 0 for lane e (and adds +0.0).
-    // Blocks of eight, the next block requested before the current one is added.
-    double acc = 0.0;
-    double v[8], w[8];
-    const double2* g2 = reinterpret_cast<const double2*>(gw);
-#pragma unroll
-    for (uint32_t j = 0; j < 4u; ++j) { const double2 q = g2[j]; v[2 * j] = q.x; v[2 * j + 1] = q.y; }
-    for (uint32_t b8 = 0; b8 < S16; b8 += 8u) {
-      const uint32_t nb8 = b8 + 8u < S16 ? b8 + 8u : b8;  // clamped prefetch
-#pragma unroll
-      for (uint32_t j = 0; j < 4u; ++j) { const double2 q = g2[(nb8 >> 1) + j]; w[2 * j] = q.x; w[2 * j + 1] = q.y; }
-      const uint32_t tb = (bm[b8 >> 5] >> (b8 & 31u)) & 0xFFu;
-      if (tb) {
-#pragma unroll
-        for (uint32_t j = 0; j < 8u; ++j) {
-          if ((tb >> j) & 1u) {
-            const uint32_t i = b8 + j;
-            int d = 0;
-            if ((uint32_t)lane < ne)
-              for (uint32_t k = 0; k < pe.n_upd; ++k)
-                if (pe.ui[k] == i) d += pe.uk[k] < 0 ? -1 : 1;
-            const uint32_t up = __ballot_sync(FULL, d > 0), dn = __ballot_sync(FULL, d < 0);
-            const uint32_t later = lane == 31 ? 0u : (0xFFFFFFFFu << (lane + 1));
-            const int n_e = (int)lds_tab<T>(X.sLen, i) - (__popc(up & later) - __popc(dn & later));
-            v[j] = X.c_alpha[i] * (double)n_e;
-          }
-        }
-      }
-#pragma unroll
-      for (uint32_t j = 0; j < 8u; ++j) acc = acc + v[j];
-#pragma unroll
-      for (uint32_t j = 0; j < 8u; ++j) v[j] = w[j];
-    }
-    const double death = P.rate_death * (double)pe.n;     // :696
-    const double M = P.rate_migration * (double)pe.n;     // :697
-    const double bd = acc + death;
-    lam = bd + M;                                          // :698
-    DP_ADD(DP_SV_WALK);
-  }
-  // The exact clock: t += e·(1/λ) over every committed iteration, with the rate of the state it ran in (:699,
-  // :701), in groups of 32 through the shared staging area; the next group's exponentials are requested
-  // before the current group is chained.
-  {
-    double t = t_exact, lam_prev = lam_exact;
-    uint32_t pos = 0;
-    uint32_t cnt = ne ? __shfl_sync(FULL, pe.m, 0) : tail_m;
-    double ex = (uint32_t)lane < cnt ? ring[lane] : 0.0;
-    for (uint32_t e = 0; e <= ne; ++e) {
-      const double theta = 1.0 / lam_prev;  // :699, the same expression the fold uses
-      const uint32_t cnt_next = e + 1 < ne ? __shfl_sync(FULL, pe.m, (int)e + 1) : (e + 1 == ne ? tail_m : 0u);
-      for (uint32_t done = 0; done < cnt; done += 32) {
-        const uint32_t left = cnt - done;
-        // what the next group will need: the rest of this segment, or the start of the next one
-        const uint32_t nleft = left > 32u ? left - 32u : cnt_next;
-        const uint32_t npos = left > 32u ? pos + done + 32u : pos + cnt;
-        const double ex_next = (uint32_t)lane < nleft ? ring[npos + (uint32_t)lane] : 0.0;
-        t = time_chain(X.sDt, lane, t, ex * theta, left >= 32u ? 31u : left - 1u);  // :701
-        ex = ex_next;
-      }
-      if (cnt == 0) ex = (uint32_t)lane < cnt_next ? ring[pos + (uint32_t)lane] : 0.0;
-      pos += cnt;
-      if (e < ne) {
-        const uint32_t n_rows = __shfl_sync(FULL, pe.n_rows, (int)e);
-        const uint32_t q0 = __shfl_sync(FULL, pe.row[0], (int)e), q1 = __shfl_sync(FULL, pe.row[1], (int)e),
-                       q2 = __shfl_sync(FULL, pe.row[2], (int)e);
-        if ((uint32_t)lane < n_rows)
-          *reinterpret_cast<double*>(X.A->log_pool + (lane == 0 ? q0 : (lane == 1 ? q1 : q2))) = t;
-        lam_prev = __shfl_sync(FULL, lam, (int)e);
-      }
-      cnt = cnt_next;
-    }
-    lam_exact = lam_prev;
-    t_exact = t;
-  }
-  __syncwarp();
-  DP_ADD(DP_SV_CHAIN);
-}
-
-// Layout of a posted batch in the server's shared slice: fourteen words per event (lane-major) in its table
-// region, the owner's clone sizes at the end of the batch in its c_len region.
-constexpr uint32_t kPendWords = 14;
-template <typename T>
-__device__ __forceinline__ T* snap_of(unsigned char* slice) { return reinterpret_cast<T*>(slice + sizeof(double) * (kSmemTable + 32)); }
-
-template <typename T>
-__device__ __forceinline__ void pend_store(uint32_t* pb, int lane, const Pend& pe) {
-  const uint32_t w[kPendWords] = {pe.m, pe.S, pe.n, pe.n_rows, pe.row[0], pe.row[1], pe.row[2], pe.n_upd,
-                                  pe.ui[0], pe.ui[1], pe.ui[2], (uint32_t)pe.uk[0], (uint32_t)pe.uk[1], (uint32_t)pe.uk[2]};
-#pragma unroll
-  for (uint32_t k = 0; k < kPendWords; ++k) pb[k * 32u + (uint32_t)lane] = w[k];
-}
-template <typename T>
-__device__ __forceinline__ void pend_load(const uint32_t* pb, int lane, Pend& pe) {
-  uint32_t w[kPendWords];
-#pragma unroll
-  for (uint32_t k = 0; k < kPendWords; ++k) w[k] = pb[k * 32u + (uint32_t)lane];
-  pe.m = w[0]; pe.S = w[1]; pe.n = w[2]; pe.n_rows = w[3]; pe.row[0] = w[4]; pe.row[1] = w[5]; pe.row[2] = w[6];
-  pe.n_upd = w[7]; pe.ui[0] = w[8]; pe.ui[1] = w[9]; pe.ui[2] = w[10];
-  pe.uk[0] = (int32_t)w[11]; pe.uk[1] = (int32_t)w[12]; pe.uk[2] = (int32_t)w[13];
-}
-
-// The batch server: an idle warp that serves the batches of one busy replicate of its block (deferred_serve on
-// the sizes snapshot and the event records the owner put into this warp's slice), so that the owner only pays
-// for the hand-over.  XO: the owner's context; XM: this warp's own context (scratch, staging area).
-template <typename T>
-__device__ __noinline__ void batch_server(Ctx<T> XO, Ctx<T> XM, volatile HelpMail* M, unsigned char* mine) {
-  const int lane = XO.lane;
-  volatile ClockChan* C = &M->clk;
-  // the owner's tables and parameters, this warp's staging area, scratch and sizes snapshot
-  Ctx<T> XS = XO;
-  XS.B = XM.B; XS.sB = XM.sB; XS.sDt = XM.sDt;
-  XS.c_len = snap_of<T>(mine); XS.sLen = smem_addr(XS.c_len);
-  XS.g_w = XM.g_w;
-  const uint32_t* pb = reinterpret_cast<const uint32_t*>(mine);
-  double t = 0.0, lam = 1.0;
-  uint32_t seq = C->done;
-  if (lane == 0) { C->warp = (uint32_t)(threadIdx.x >> 5); __threadfence_block(); C->attached = 1; }
-  __syncwarp();
-  for (;;) {
-    while (C->posted == seq) {
-      if (M->done) return;
-      __nanosleep(20);
-    }
-    __threadfence_block();
-    ++seq;
-    const uint32_t ne = C->ne, tail_m = C->tail_m, S = C->S, ring_off = C->ring_off;
-    if (C->init) { t = C->t_init; lam = C->lam_init; }
-    Pend pe;
-    pend_load<T>(pb, lane, pe);
-    __syncwarp();
-    deferred_serve(XS, S, pe, ne, tail_m, reinterpret_cast<const double*>(XO.samp) + ring_off, lam, t);
-    if (lane == 0) {
-      C->t_exact = t;
-      C->lam_exact = lam;
-      __threadfence_block();
-      C->done = seq;
-    }
-    __syncwarp();
-  }
-}
-
-// Runs rounds on the approximate table and clock until the exact state is needed again: a time that matters
-// comes within reach, a draw lands in the guard band, or the replicate ends.  On return the clock is exact and
-// the table is marked dirty from clone 0 (the exact loop re-folds it); returns true when the replicate is over
-// (extinction or an error status).
-template <typename T>
-__device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile HelpMail* M, const int my_warp, const bool srv_ok,
-                                          const double Tf, const uint64_t max_iter, const double watch_snap, const double watch_tb) {
+__device__ __noinline__ bool run_decoupled(Ctx<T>& Xref, Rep& rref, volatile HelpMail* M, const int my_warp, const double Tf,
+                                           const uint64_t max_iter, const double watch_snap, const double watch_tb) {
   Ctx<T> X = Xref;
   Rep r = rref;
   const RunArgs& A = *X.A;
   const DevPoint& P = *X.P;
   const int lane = X.lane;
-  // unit exponentials of the committed iterations (excision scratch), two halves: one being filled, one being served
-  double* const ring_base = reinterpret_cast<double*>(X.samp);
-  const uint32_t ring_cap = (A.g.nv / 4u) & ~1u;
-  uint32_t ring_half = 0;
-  double* ring = ring_base;
-  uint32_t ring_n = 0, ne = 0, seg_m = 0;
-  bool outstanding = false;  // a batch is with the server: lam_exact / t_exact are the server's until it is collected
-  double lam_exact = r.lambda, t_exact = r.t;  // the state is exact and clean on entry
-  Pend pe;
-  pe.m = pe.S = pe.n = pe.n_rows = pe.n_upd = 0;
-  pe.row[0] = pe.row[1] = pe.row[2] = pe.ui[0] = pe.ui[1] = pe.ui[2] = 0;
-  pe.uk[0] = pe.uk[1] = pe.uk[2] = 0;
+  uint32_t hw = 0;
+  if (lane == 0) hw = M->clk.warp;
+  hw = __shfl_sync(FULL, hw, 0);
+  unsigned char* fh_slice = slice_of(X.B, my_warp, A.smem_per_warp, hw);
+  volatile ClockMsg* ring = ring_of<T>(fh_slice);
+  { Ctx<T> xc = X; Rep rc = r; dec_enter(xc, rc, M, ring); }
   r.guard = ((P.quirks & JSB_QUIRK_DEBUG_WIDE_GUARD) ? 1e-3 : 2.0 * kGuardEps) * r.lambda;
   uint32_t dec_events = 0;  // events since the approximate table was re-based on the exact one
   bool finished = false;
-  if (lane == 0) atomicAdd(A.work_counter + 2, 1ull);  // statistics: entries into deferred mode (JSB_TIMING)
-
-  volatile ClockChan* C = M ? &M->clk : nullptr;
-  auto collect = [&]() {  // wait for the server, take the exact clock and rate back
-    if (!outstanding) return;
-    while (C->done != C->posted) __nanosleep(20);
-    __threadfence_block();
-    t_exact = C->t_exact;
-    lam_exact = C->lam_exact;
-    outstanding = false;
-  };
-  auto serve = [&]() {  // this warp serves what is pending (events and tail)
-    collect();
-    DP_T0();
-    deferred_serve(X, r.S, pe, ne, seg_m, ring, lam_exact, t_exact);
-    DP_ADD(DP_SERVE);
-    r.t = t_exact;
-    ring_n = 0; ne = 0; seg_m = 0;
-  };
-  auto hand_over = [&]() -> bool {  // a full batch goes to the server warp, if one is attached
-    if (!srv_ok || C->attached == 0) return false;
-    DP_T0();
-    const bool init = !outstanding;
-    if (outstanding) {  // one batch in flight at a time: the previous one must be done (it usually is)
-      while (C->done != C->posted) __nanosleep(20);
-      __threadfence_block();
-    }
-    uint32_t hw = 0;
-    if (lane == 0) hw = C->warp;
-    hw = __shfl_sync(FULL, hw, 0);
-    unsigned char* slice = slice_of(X.B, my_warp, A.smem_per_warp, hw);
-    T* snap = snap_of<T>(slice);
-    for (uint32_t i = (uint32_t)lane; i < r.S; i += 32) snap[i] = X.c_len[i];
-    pend_store<T>(reinterpret_cast<uint32_t*>(slice), lane, pe);
-    __syncwarp();
-    if (lane == 0) {
-      C->ne = ne; C->tail_m = 0; C->S = r.S; C->ring_off = ring_half * ring_cap; C->init = init ? 1u : 0u;
-      if (init) { C->t_init = t_exact; C->lam_init = lam_exact; }
-      __threadfence_block();
-      C->posted = C->posted + 1u;
-    }
-    __syncwarp();
-    outstanding = true;
-    ring_half ^= 1u;
-    ring = ring_base + ring_half * ring_cap;
-    ring_n = 0; ne = 0;
-    DP_ADD(DP_SERVE);
-    return true;
-  };
 
   for (;;) {
     if (r.n == 0) { finished = true; break; }  // extinction; the approximate clock never reaches Tf in here
-    if (ne == 32u && seg_m == 0) { if (!hand_over()) serve(); }
-    else if (ne == 32u || ring_n + 32u * (1u + (uint32_t)kMaxLook) > ring_cap) serve();
-    if (dec_events >= kApproxResync) {         // re-base the approximate table on the exact one (sizes are exact)
-      DP_T0();
-      r.dirty_from = 0;
-      refold(X, r);
-      DP_ADD(DP_RESYNC);
+    if (dec_events >= kClockResync) {          // re-base the approximate table and clock
+      { Ctx<T> xc = X; Rep rc = r; dec_leave(xc, rc, M, fh_slice); r = rc; }
+      { Ctx<T> xc = X; Rep rc = r; dec_enter(xc, rc, M, ring); }
       r.guard = ((P.quirks & JSB_QUIRK_DEBUG_WIDE_GUARD) ? 1e-3 : 2.0 * kGuardEps) * r.lambda;
       dec_events = 0;
     }
-    // ---- lookahead requests, as in the exact loop; θ = 1 so that the helpers return unit exponentials ----
+    // ---- lookahead requests, as in the exact loop (the rate they get is the approximate one) ----
     uint32_t nposted = 0, reqid = 0;
-    if (M) {
+    {
       if (lane == 0) {
         const uint32_t nh = M->nhelp;
         nposted = nh;
@@ -2260,7 +2127,7 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
         if (lane == 0) {
           M->S = r.S; M->n = r.n; M->search_top = X.search_top; M->stream = X.key.stream;
           M->it_base = r.it;
-          M->lambda = r.lambda; M->guard = r.guard; M->theta = 1.0;
+          M->lambda = r.lambda; M->guard = r.guard; M->theta = r.theta;
           __threadfence_block();
           M->word = (reqid << 8) | nposted;
         }
@@ -2273,14 +2140,13 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
       __threadfence_block();
     };
 
-    double ev[kMaxSub];
+    double dtv[kMaxSub];
     uint32_t effm[kMaxSub], cls[kMaxSub], xx[kMaxSub], cell[kMaxSub], pos[kMaxSub];
-    DP_T0();
-    if (!batch_eval<T, 1>(X, r, false, FULL, ev, effm, cls, xx, cell, pos, true)) {
+    if (!batch_eval<T, 1>(X, r, false, FULL, dtv, effm, cls, xx, cell, pos, true)) {
       wait_acks();  // a draw inside the guard band: the exact loop decides this round
       break;
     }
-    DP_ADD(DP_EVAL);
+    dtv[0] = dtv[0] * r.theta;
     bool found = effm[0] != 0;
     uint32_t jE = found ? (uint32_t)__ffs(effm[0]) - 1u : 31u;
 
@@ -2294,14 +2160,14 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
       if (watch_tb > lo && watch_tb <= hi) sl = true;
       return sl;
     };
-    double span = (uint32_t)lane <= jE ? ev[0] : 0.0;
+    double span = (uint32_t)lane <= jE ? dtv[0] : 0.0;
     for (int d = 16; d > 0; d >>= 1) span += __shfl_xor_sync(FULL, span, d);
-    double t1 = r.t + span * r.theta;
+    double t1 = r.t + span;
     if (may_touch(t1, (uint64_t)jE + 1u)) {
       wait_acks();
       break;
     }
-    uint32_t adv = 0;
+    uint64_t adv = 0;
     int from_helper = -1;
     if (nposted) {
       wait_acks();
@@ -2310,8 +2176,8 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
         if (!R->usable) break;
         const uint32_t effm2 = R->effm;
         const uint32_t jE2 = effm2 ? (uint32_t)__ffs(effm2) - 1u : 31u;
-        const double t2 = t1 + R->sum_dt * r.theta;
-        if (may_touch(t2, (uint64_t)adv + 32u + jE2 + 1u)) break;
+        const double t2 = t1 + R->sum_dt;
+        if (may_touch(t2, adv + 32u + jE2 + 1u)) break;
         adv += 32u;
         t1 = t2;
         jE = jE2;
@@ -2319,26 +2185,18 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
         from_helper = (int)h;
       }
     }
-    DP_ADD(DP_HELP);
-    // keep the unit exponentials of the committed iterations, in iteration order
-    ring[ring_n + (uint32_t)lane] = ev[0];
-    for (uint32_t h = 0; h * 32u < adv; ++h) ring[ring_n + 32u * (h + 1u) + (uint32_t)lane] = M->res[h].dt[lane];
-    const uint32_t m_commit = adv + jE + 1u;
-    ring_n += m_commit;
-    seg_m += m_commit;
+    const uint64_t it_first = r.it;
+    const uint32_t m_commit = (uint32_t)adv + jE + 1u;
     r.it += m_commit;
-    r.t = t1;  // approximate; the log records written below get the exact time when the batch is served
-    __syncwarp();
-    DP_ADD(DP_COMMIT);
+    r.t = t1;  // approximate; the log records written below get the exact time from the helper
 
     // ---- the event, and what it does to the clone sizes -----------------------------------------
-    if (!found) continue;
     bool keep_going = true;
     const uint32_t S_old = r.S, chunk0 = r.cur_chunk;
     const uint64_t nlog0 = r.nlog;
     uint32_t u_i0 = kNone, u_i1 = kNone;  // existing clones whose size changes (by -1 / +1)
     double u_a0 = 0.0, u_a1 = 0.0;        // the signed change of their class weight
-    {
+    if (found) {
       Eval ej;
       if (from_helper >= 0) {
         volatile HelpRes* R = &M->res[from_helper];
@@ -2351,20 +2209,18 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
       }
       ej.occ = (ej.cls < r.S && P.rule != JSB_RULE_CONTACT) ? (uint32_t)X.clone[ej.pos] : 0u;
       ej.effective = true;
-      if (ej.cls == r.S + 1) { apply_migration(X, r, ej); DP_ADD(DP_MIGR); }
+      if (ej.cls == r.S + 1) apply_migration(X, r, ej);
       else if (ej.cls == r.S) {
         const uint32_t cl = apply_death(X, r, ej);
         u_i0 = cl - 1u; u_a0 = -X.c_alpha[cl - 1u];
-        DP_ADD(DP_DEATH);
       } else {
         // requested before the event so that the loads are back when it is done
         u_i1 = ej.cls; u_a1 = X.c_alpha[ej.cls];
         if (ej.occ) { u_i0 = ej.occ - 1u; u_a0 = -X.c_alpha[ej.occ - 1u]; }
         keep_going = apply_birth(X, r, ej);
-        DP_ADD(DP_BIRTH);
       }
     }
-    // ---- remember what this event did; move the approximate table --------------------------------
+    // ---- tell the clock helper what this round did; move the approximate table -----------------
     const bool has_new = r.S > S_old;
     if (has_new) { u_i1 = kNone; u_a1 = 0.0; }  // a driver birth leaves the parent clone's size unchanged
     if (u_i0 == u_i1) { u_i0 = u_i1 = kNone; u_a0 = u_a1 = 0.0; }  // a cell displaced by its own clone: no change
@@ -2377,44 +2233,29 @@ __device__ __noinline__ bool run_deferred(Ctx<T>& Xref, Rep& rref, volatile Help
       const uint32_t ch = (pr / kLogChunk == (r.nlog - 1) / kLogChunk) ? r.cur_chunk : chunk0;
       rows[k] = ch * kLogChunk + (uint32_t)(pr % kLogChunk);
     }
-    const bool changed = keep_going && r.dirty_from != kNone;
-    if ((uint32_t)lane == ne) {
-      pe.m = seg_m; pe.S = r.S; pe.n = r.n;
-      pe.n_rows = n_rows; pe.row[0] = rows[0]; pe.row[1] = rows[1]; pe.row[2] = rows[2];
-      uint32_t nu = 0;
-      if (changed) {
-        if (u_i0 != kNone) { pe.ui[nu] = u_i0; pe.uk[nu] = -1; ++nu; }
-        if (u_i1 != kNone) { pe.ui[nu] = u_i1; pe.uk[nu] = 1; ++nu; }
-        if (has_new) { pe.ui[nu] = S_old; pe.uk[nu] = 2; ++nu; }
-      }
-      pe.n_upd = nu;
-    }
-    ++ne;
-    seg_m = 0;
-    DP_ADD(DP_BOOK);
-    if (changed) {
+    const uint32_t from = keep_going ? r.dirty_from : kNone;
+    uint32_t n_upd = 0, ui[3] = {0u, 0u, 0u};
+    int uk[3] = {0, 0, 0};
+    if (u_i0 != kNone) { ui[n_upd] = u_i0; uk[n_upd] = -1; ++n_upd; }
+    if (u_i1 != kNone) { ui[n_upd] = u_i1; uk[n_upd] = 1; ++n_upd; }
+    if (has_new) { ui[n_upd] = S_old; uk[n_upd] = 2; ++n_upd; }
+    clock_post(M, ring, lane, 1u, it_first, m_commit, from, r.S, r.n, n_rows, rows[0], rows[1], rows[2], n_upd, ui[0], uk[0],
+               ui[1], uk[1], ui[2], uk[2]);
+    if (from != kNone) {
       const double new_alpha = has_new ? X.c_alpha[S_old] : 0.0;
       Ctx<T> xc = X; Rep rc = r;
       approx_update(xc, rc, S_old, u_i0, u_a0, u_i1, u_a1, has_new, new_alpha);
       r = rc; X.search_top = xc.search_top;
       ++dec_events;
-      DP_ADD(DP_APPROX);
     }
     if (!keep_going || r.status == JSB_ST_INTERNAL) { finished = true; break; }
   }
-  serve();
-  r.lambda = lam_exact;
-  r.theta = 1.0 / lam_exact;
-  r.dirty_from = 0;  // the exact loop re-folds the whole table
-  r.exact_valid = false;
+  { Ctx<T> xc = X; Rep rc = r; dec_leave(xc, rc, M, fh_slice); r = rc; }
   Xref.search_top = X.search_top;
   rref = r;
   return finished;
 }
 
-// ---------------------------------------------------------------------------------------------
-// One replicate
-// ---------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, const int my_warp) {
   const RunArgs& A = *X.A;
@@ -2460,14 +2301,8 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, c
   };
   reload_watch();
 
-  // deferred mode needs room for the unit exponentials of a batch in the excision scratch array
-  const bool ring_fits = nv / 4u >= 64u * (1u + (uint32_t)kMaxLook);
-  const bool dec_allowed = (A.defer != 0 || (P.quirks & JSB_QUIRK_DEBUG_DECOUPLE) != 0) && !force_exact && width == 32u &&
-                           A.pilot_iters == 0 && ring_fits;
-  const bool clk_allowed = M != nullptr && (A.helpers & 2u) == 0 && A.pilot_iters == 0 && ring_fits;
-  const bool debug_dec = (P.quirks & JSB_QUIRK_DEBUG_DECOUPLE) != 0;
-  const uint32_t dec_min_clones = debug_dec ? 1u : (A.dec_min_clones < A.defer_min_clones ? A.dec_min_clones : A.defer_min_clones);
-  const uint32_t defer_min_clones = debug_dec ? 1u : A.defer_min_clones;
+  const bool dec_allowed = M != nullptr && (A.helpers & 2u) == 0 && A.pilot_iters == 0;
+  const uint32_t dec_min_clones = (P.quirks & JSB_QUIRK_DEBUG_DECOUPLE) ? 1u : A.dec_min_clones;
   uint64_t dec_hold = 0;  // no (re-)entry into decoupled mode before this iteration
 
   PROF_DECL
@@ -2484,11 +2319,8 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, c
 #endif
     if (r.dirty_from != kNone) { refold(X, r); PROF_ADD(PH_REFOLD); }
 
-    // ---- enough clones for the exact fold to hurt: run on the approximate table and clock until something
-    // needs the exact ones (a clock helper warp keeps the exact ones if one is attached, else they are served
-    // in batches by this warp)
-    if (r.S >= dec_min_clones && r.it >= dec_hold &&
-        ((dec_allowed && r.S >= defer_min_clones) || (clk_allowed && M->clk.attached != 0)) &&
+    // ---- a clock helper is attached: run on the approximate clock until something needs the exact one
+    if (dec_allowed && r.S >= dec_min_clones && r.it >= dec_hold && M->clk.attached != 0 &&
         !(tree_quirk && r.it + 1 < (uint64_t)n_bott) &&
         !(max_iter && r.it + 4096u >= max_iter)) {
       want_dec = true;  // handled outside this loop: the call must not shape its register allocation
@@ -2659,8 +2491,9 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, c
   }
   if (!want_dec) break;
   {
+    // ---- a clock helper is attached: run on the approximate clock until something needs the exact one
     Ctx<T> xc = X; Rep rc = r;
-    const bool finished = run_deferred(xc, rc, M, my_warp, clk_allowed, Tf, max_iter, watch_snap, watch_tb);
+    const bool finished = run_decoupled(xc, rc, M, my_warp, Tf, max_iter, watch_snap, watch_tb);
     r = rc; X.search_top = xc.search_top;
     dec_hold = r.it + 1024u;
     if (finished) break;
@@ -2669,10 +2502,6 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, c
 #ifdef JSB_PROFILE
   if (lane == 0 && (X.local_idx < 2 || r.it > 6000000ull)) {
     printf("sub-phases: refold A %lld B %lld tail %lld\n", g_sub[0], g_sub[1], g_sub[2]);
-    printf("deferred: eval %lld/%lld help %lld commit %lld | death %lld/%lld birth %lld/%lld migr %lld/%lld | book %lld approx %lld/%lld | serve %lld/%lld (A %lld walk %lld chain %lld) resync %lld/%lld\n",
-           g_dp[DP_EVAL], g_dpn[DP_EVAL], g_dp[DP_HELP], g_dp[DP_COMMIT], g_dp[DP_DEATH], g_dpn[DP_DEATH], g_dp[DP_BIRTH], g_dpn[DP_BIRTH],
-           g_dp[DP_MIGR], g_dpn[DP_MIGR], g_dp[DP_BOOK], g_dp[DP_APPROX], g_dpn[DP_APPROX], g_dp[DP_SERVE], g_dpn[DP_SERVE],
-           g_dp[DP_SV_A], g_dp[DP_SV_WALK], g_dp[DP_SV_CHAIN], g_dp[DP_RESYNC], g_dpn[DP_RESYNC]);
     printf("rep %lld it %llu rounds %lld eff %u S %u n %u | refold %lld/%lld (elems %lld) draws %lld/%lld class %lld eval %lld time %lld | birth %lld/%lld death %lld/%lld migr %lld/%lld exc %lld\n",
            (long long)X.local_idx, (unsigned long long)r.it, prof_n[PH_EVAL], r.n_eff, r.S, r.n, prof_c[PH_REFOLD], prof_n[PH_REFOLD], prof_fold,
            prof_c[PH_DRAWS], prof_n[PH_DRAWS], prof_c[PH_CLASS], prof_c[PH_EVAL], prof_c[PH_TIME], prof_c[PH_BIRTH],
@@ -2762,7 +2591,7 @@ __global__ void __launch_bounds__(MAXT, 1) ssa_kernel(const __grid_constant__ Ru
   volatile HelpMail* myM = mail_of(s_dyn, A.smem_per_warp, warp);
   if (lane == 0) {
     myM->word = 0; myM->nhelp = 0; myM->done = 0;
-    myM->clk.attached = 0; myM->clk.warp = 0; myM->clk.posted = 0; myM->clk.done = 0; myM->clk.claimed = 0; myM->clk.init = 0;
+    myM->clk.attached = 0; myM->clk.warp = 0; myM->clk.posted = 0; myM->clk.done = 0; myM->clk.claimed = 0;
     for (int h = 0; h < kMaxLook; ++h) myM->res[h].ack = 0;
   }
   __syncthreads();  // the only block-wide barrier: mailboxes are initialised before anyone looks
@@ -2856,7 +2685,7 @@ __global__ void __launch_bounds__(MAXT, 1) ssa_kernel(const __grid_constant__ Ru
     if (target < 0) break;
     DevPoint* oP;
     Ctx<T> XO = make_ctx<T>(A, s_dyn, target, lane, &oP);
-    if (role == 0u) batch_server<T>(XO, X, mail_of(s_dyn, A.smem_per_warp, target), s_dyn + (size_t)warp * A.smem_per_warp);
+    if (role == 0u) clock_serve<T>(XO, mail_of(s_dyn, A.smem_per_warp, target), s_dyn + (size_t)warp * A.smem_per_warp);
     else helper_serve<T>(XO, mail_of(s_dyn, A.smem_per_warp, target), role - 1u);
   }
 }
