@@ -106,7 +106,14 @@ struct RunArgs {
   uint64_t pilot_iters;   // > 0: pilot pass (no outputs except prio)
   unsigned long long* trace;  // JSB_TRACE: per replicate {start ns, end ns, sm<<8|warp, iterations}
   float* prio;
+  // Suspending pilot: the pilot pass runs with every output on, parks the state of each replicate that reaches
+  // `pilot_iters` in `susp` (its slot workspace + registers + shared tables) and finishes the others; the full
+  // pass resumes the parked ones.  Same draws, same order: the trajectory does not know it was interrupted.
+  uint8_t* susp;            // [n_local][susp_stride]; nullptr: the pilot pass is thrown away (old behaviour)
+  uint64_t susp_stride;     // ws_stride + susp_extra_bytes(site_bytes)
+  uint32_t* susp_state;     // [n_local] 0 = not started, 1 = parked, 2 = finished in the pilot pass
 };
+__host__ __device__ inline uint64_t susp_extra_bytes(uint32_t site_bytes) { return 256 + 128 + 2ull * kTab * site_bytes; }
 
 __host__ __device__ inline uint64_t jsb_align16(uint64_t x) { return (x + 15) & ~uint64_t(15); }
 __host__ __device__ inline WsLayout ws_layout(uint32_t nv, uint32_t arena_cap, uint32_t site_bytes) {

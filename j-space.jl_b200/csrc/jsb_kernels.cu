@@ -314,6 +314,7 @@ struct Ctx {
   int64_t local_idx;
   int lane;
   bool track_ids;           // cell ids are only maintained when the log or the lattice is wanted
+  uint8_t* ws_base;         // this warp slot's workspace (suspend / resume copies)
 };
 
 struct Rep {
@@ -325,6 +326,8 @@ struct Rep {
   uint32_t n_eff, n_births, n_deaths, n_migr, n_disp, n_exc;
   bool log_on, exact_valid;
 };
+
+static_assert(sizeof(Rep) <= 256, "susp_save parks Rep in a 256-byte block");
 
 __device__ __forceinline__ void mark_dirty(Rep& r, uint32_t clone_idx) {
   r.dirty_from = clone_idx < r.dirty_from ? clone_idx : r.dirty_from;
@@ -2256,6 +2259,80 @@ __device__ __noinline__ bool run_decoupled(Ctx<T>& Xref, Rep& rref, volatile Hel
   return finished;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Suspending pilot (RunArgs::susp).  A replicate that reaches the pilot depth is parked: the live part of its
+// slot workspace, the Rep registers, the per-lane label bitmap and the shared per-clone tables go to
+// susp[local_idx]; the full pass copies them back into whatever slot picks the replicate up, rebuilds the
+// occupancy bitmask from clone[] and re-folds the class boundaries from clone 0 (the sequential fold is
+// deterministic), and carries on at iteration it + 1.  Draws are addressed by iteration number, so the
+// trajectory is the one an uninterrupted run produces.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_copy16(uint8_t* dst, const uint8_t* src, uint64_t bytes, int lane) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint64_t n = (bytes + 15) >> 4;
+  uint64_t i = (uint64_t)lane;
+  for (; i + 96 < n; i += 128) {
+    const uint4 a = __ldcs(s + i), b = __ldcs(s + i + 32), c = __ldcs(s + i + 64), e = __ldcs(s + i + 96);
+    __stcs(d + i, a); __stcs(d + i + 32, b); __stcs(d + i + 64, c); __stcs(d + i + 96, e);
+  }
+  for (; i < n; i += 32) __stcs(d + i, __ldcs(s + i));
+}
+template <typename T>
+__device__ __noinline__ void susp_copy(const Ctx<T>& X, uint32_t arena_top, bool save) {
+  const RunArgs& A = *X.A;
+  uint8_t* park = A.susp + (uint64_t)X.local_idx * A.susp_stride;
+  uint8_t* ws = X.ws_base;
+  const uint64_t live = A.L.arena + (uint64_t)arena_top * sizeof(T);   // clone, cellid, cs_alive, heads, hints, arena in use
+  const uint64_t tab0 = A.L.c_cnt, tab1 = A.L.g_w;                     // per-clone tables kept in global memory
+  if (save) { warp_copy16(park, ws, live, X.lane); warp_copy16(park + tab0, ws + tab0, tab1 - tab0, X.lane); }
+  else { warp_copy16(ws, park, live, X.lane); warp_copy16(ws + tab0, park + tab0, tab1 - tab0, X.lane); }
+}
+template <typename T>
+__device__ __noinline__ void susp_save(const Ctx<T>& X, const Rep& r) {
+  const RunArgs& A = *X.A;
+  __syncwarp();
+  susp_copy(X, r.arena_top, true);
+  uint8_t* blk = A.susp + (uint64_t)X.local_idx * A.susp_stride + A.ws_stride;
+  if (X.lane == 0) *reinterpret_cast<Rep*>(blk) = r;
+  reinterpret_cast<uint32_t*>(blk + 256)[X.lane] = r.used_w;
+  T* tl = reinterpret_cast<T*>(blk + 384);
+  for (uint32_t i = X.lane; i < r.S; i += 32) { tl[i] = X.c_len[i]; tl[kTab + i] = X.c_off8[i]; }
+  __threadfence();
+  __syncwarp();
+  if (X.lane == 0) A.susp_state[X.local_idx] = 1u;
+}
+template <typename T>
+__device__ __noinline__ void susp_restore(Ctx<T>& X, Rep& r) {
+  const RunArgs& A = *X.A;
+  const uint8_t* blk = A.susp + (uint64_t)X.local_idx * A.susp_stride + A.ws_stride;
+  r = *reinterpret_cast<const Rep*>(blk);
+  r.used_w = reinterpret_cast<const uint32_t*>(blk + 256)[X.lane];
+  susp_copy(X, r.arena_top, false);
+  const T* tl = reinterpret_cast<const T*>(blk + 384);
+  for (uint32_t i = X.lane; i < r.S; i += 32) { X.c_len[i] = tl[i]; X.c_off8[i] = tl[kTab + i]; }
+  for (uint32_t i = X.lane; i < (uint32_t)kSmemTable; i += 32) X.B[i] = __longlong_as_double(0x7ff0000000000000ll);  // +inf pad
+  __syncwarp();  // the workspace copy above is visible to the whole warp
+  if (X.occ) {
+    const uint32_t nv = A.g.nv;
+    for (uint32_t w = X.lane; w < A.occ_words; w += 32) {
+      uint32_t bits = 0;
+      const uint32_t s0 = w * 32u;
+      for (uint32_t k = 0; k < 32u && s0 + k < nv; k += 2) {  // clone[] is u16: two sites per 32-bit load (nv + 1 entries are allocated)
+        const uint32_t two = *reinterpret_cast<const uint32_t*>(X.clone + s0 + k);
+        bits |= (uint32_t)((two & 0xFFFFu) != 0u) << k;
+        if (s0 + k + 1 < nv) bits |= (uint32_t)((two >> 16) != 0u) << (k + 1);
+      }
+      X.occ[w] = bits;
+    }
+  }
+  r.dirty_from = 0;
+  r.exact_valid = false;
+  r.status = JSB_ST_OK;
+  X.search_top = 2;
+  __syncwarp();
+}
+
 template <typename T>
 __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, const int my_warp) {
   const RunArgs& A = *X.A;
@@ -2267,11 +2344,15 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, c
   r.snap_idx = 0;
   r.status = JSB_ST_OK;
   r.n_eff = r.n_births = r.n_deaths = r.n_migr = r.n_disp = r.n_exc = 0;
-  r.log_on = (A.flags & JSB_OUT_EVENTS) != 0 && A.pilot_iters == 0;
+  r.log_on = (A.flags & JSB_OUT_EVENTS) != 0 && (A.pilot_iters == 0 || A.susp != nullptr);
   r.exact_valid = false;
   r.dirty_from = 0;
   X.search_top = 2;
-  { Ctx<T> xc = X; Rep rc = r; seed_replicate(xc, rc); r = rc; }
+  if (A.susp && A.pilot_iters == 0 && A.susp_state[X.local_idx] == 1u) {  // parked by the pilot pass: carry on
+    Ctx<T> xc = X; Rep rc = r; susp_restore(xc, rc); r = rc; X.search_top = xc.search_top;
+  } else {
+    Ctx<T> xc = X; Rep rc = r; seed_replicate(xc, rc); r = rc;
+  }
 
   const bool intent = (P.quirks & JSB_QUIRK_EXCISION_INTENT) != 0;
   const bool force_exact = (P.quirks & JSB_QUIRK_DEBUG_EXACT_CLASSES) != 0;
@@ -2510,8 +2591,12 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, c
 #endif
   if (A.pilot_iters) {
     // work estimate for longest-first scheduling: iterations left if the total rate stayed as it is
-    if (lane == 0) A.prio[X.local_idx] = (r.n > 0 && r.t < P.Tf) ? (float)(r.lambda * (P.Tf - r.t)) : 0.0f;
-    return;
+    const uint64_t user_max = A.points[(A.g_begin + X.local_idx) / A.reps_per_point].max_iter;
+    const bool capped = r.status == JSB_ST_MAX_ITER && !(user_max && r.it >= user_max);  // stopped by the pilot depth only
+    if (lane == 0) A.prio[X.local_idx] = (A.susp ? capped : (r.n > 0 && r.t < P.Tf)) ? (float)(r.lambda * (P.Tf - r.t)) : 0.0f;
+    if (!A.susp) return;
+    if (capped) { Ctx<T> xc = X; Rep rc = r; rc.status = JSB_ST_OK; susp_save(xc, rc); return; }
+    if (lane == 0) A.susp_state[X.local_idx] = 2u;  // over before the pilot depth: outputs below, nothing left for the full pass
   }
   { Ctx<T> xc = X; Rep rc = r; write_outputs(xc, rc); }
 }
@@ -2537,6 +2622,7 @@ __device__ __forceinline__ Ctx<T> make_ctx(const RunArgs& A, unsigned char* s_dy
   Ctx<T> X;
   X.A = &A;
   X.lane = lane;
+  X.ws_base = base;
   X.clone = reinterpret_cast<uint16_t*>(base + L.clone);
   X.cellid = reinterpret_cast<uint32_t*>(base + L.cellid);
   X.Alist = reinterpret_cast<T*>(base + L.A);
@@ -2614,6 +2700,7 @@ __global__ void __launch_bounds__(MAXT, 1) ssa_kernel(const __grid_constant__ Ru
     }
     if ((long long)idx >= A.n_local) break;
     if (A.order) idx = A.order[idx];
+    if (A.susp && A.pilot_iters == 0 && A.susp_state[idx] == 2u) continue;  // finished inside the pilot pass
     const int64_t gidx = A.g_begin + (int64_t)idx;
     X.local_idx = (int64_t)idx;
     X.key.stream = (uint32_t)gidx;

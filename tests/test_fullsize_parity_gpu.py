@@ -50,11 +50,32 @@ def test_pilot_order_and_counter_path_vs_oracle(jsb, oracle, monkeypatch):
     # replicate against the oracle; and the same ensemble without the pilot must give identical summaries
     p = dict(C2, Tf=70.0, t_bottleneck=[30.0])
     monkeypatch.setenv("JSB_DEBUG_GRID", "4")
+    monkeypatch.setenv("JSB_PILOT_ITERS", "300")
     a, b = [], []
     compare_runs(jsb, oracle, ("lattice", 2, 40, 40), p, seed=77, reps=48, warps_per_sm=2, summaries_out=a)
     monkeypatch.setenv("JSB_NO_PILOT", "1")
     compare_runs(jsb, oracle, ("lattice", 2, 40, 40), p, seed=77, reps=48, warps_per_sm=2, summaries_out=b, only=[0, 5])
     assert a[0].tobytes() == b[0].tobytes()
+    # the pilot pass parks every replicate that reaches its depth (300 iterations here) and the full pass resumes
+    # it: most of these replicates were interrupted once.  A pilot pass that is thrown away must give the same.
+    assert int((a[0]["n_iterations"] > 300).sum()) > 24
+    monkeypatch.delenv("JSB_NO_PILOT")
+    monkeypatch.setenv("JSB_NO_SUSPEND", "1")
+    c = []
+    compare_runs(jsb, oracle, ("lattice", 2, 40, 40), p, seed=77, reps=48, warps_per_sm=2, summaries_out=c, only=[0, 5])
+    assert a[0].tobytes() == c[0].tobytes()
+
+
+def test_suspended_replicates_resume_with_snapshots_and_small_arena(jsb, oracle, monkeypatch):
+    # resume with everything that lives across the interruption: snapshot index, excision index, event-log
+    # chunks, a list arena that has been compacted, voter displacements
+    p = dict(C2, Tf=60.0, rule="voter", t_bottleneck=[20.0, 40.0], ratio_bottleneck=[0.5, 0.5], t_snapshot=[5.0, 25.0, 55.0])
+    monkeypatch.setenv("JSB_DEBUG_GRID", "3")
+    monkeypatch.setenv("JSB_PILOT_ITERS", "256")
+    monkeypatch.setenv("JSB_DEBUG_ARENA_ENTRIES", "16000")
+    got = []
+    compare_runs(jsb, oracle, ("lattice", 2, 36, 36), p, seed=5, reps=40, warps_per_sm=2, summaries_out=got)
+    assert np.all(got[0]["status"] == 0) and int((got[0]["n_iterations"] > 256).sum()) > 15
 
 
 @pytest.mark.parametrize("rule", ["contact", "hvoter"])
