@@ -73,6 +73,16 @@ void* pinned_take(size_t bytes, size_t* got) {
   return p;
 }
 
+// the cached block, whatever its size (streamed outputs write into it while the kernel is still running)
+void* pinned_take_cached(size_t* got) {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  void* p = g_pin_ptr;
+  *got = g_pin_bytes;
+  g_pin_ptr = nullptr;
+  g_pin_bytes = 0;
+  return p;
+}
+
 void pinned_give(void* p, size_t bytes) {
   if (!p) return;
   void* drop = nullptr;
@@ -398,7 +408,8 @@ struct jsb_result {
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   jsb_event* events = nullptr;  // replicate-major
-  std::vector<uint64_t> ev_off;  // n_local + 1
+  std::vector<uint64_t> ev_off;  // n_local + 1: first row of every replicate (streamed outputs: in finish order)
+  std::vector<uint64_t> ev_cnt;  // n_local: rows of every replicate
   uint16_t* lat_clone = nullptr;
   uint32_t* lat_cell = nullptr;
   uint32_t* lists = nullptr;
@@ -693,6 +704,13 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
   long long* d_clone_off = nullptr;
   jsb_event *d_log = nullptr, *d_gather = nullptr;
   uint32_t* d_chunk_next = nullptr;
+  uint4* d_fin = nullptr;               // [n_local] fin_list (streamed outputs)
+  uint32_t* d_chunk_prev = nullptr;
+  unsigned long long* d_fin_ctr = nullptr;
+  cudaStream_t stream2 = nullptr;
+  void* h_fin = nullptr;                // pinned: fin_list copy + counter + chunk_next
+  bool streamed = false;                // the event log reached the host while the kernel was running
+  std::vector<uint4> fin_host;
   int32_t* d_chunk_owner = nullptr;
   uint32_t* d_chunk_seq = nullptr;
   unsigned long long* d_ev_off = nullptr;
@@ -890,6 +908,31 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
     a.snaps = d_snaps; a.max_snap = max_snap;
     a.out_clone = d_out_clone; a.out_cell = d_out_cell; a.out_lists = d_out_lists;
     a.work_counter = d_counters;
+    // Streamed outputs (exact kernel, event log requested; see the loop after the launch): needs the pinned host
+    // block and the gather buffer of an earlier call, because the sizes are only known afterwards.
+    const size_t b_lc0 = (opts->flags & JSB_OUT_LATTICE) ? ((sizeof(uint16_t) * (size_t)g->nv * n_local + 255) & ~size_t(255)) : 0;
+    const size_t b_li0 = (opts->flags & JSB_OUT_LATTICE) ? ((sizeof(uint32_t) * (size_t)g->nv * n_local + 255) & ~size_t(255)) : 0;
+    const size_t b_ls0 = (opts->flags & JSB_OUT_LISTS) ? ((sizeof(uint32_t) * 2 * (size_t)g->nv * n_local + 255) & ~size_t(255)) : 0;
+    bool want_stream = (opts->flags & JSB_OUT_EVENTS) && !fast_mode && !std::getenv("JSB_NO_STREAM_OUT") && ds.buf[BUF_GATHER].p;
+    jsb_event* h_events = nullptr;
+    if (want_stream) {
+      res->pinned = pinned_take_cached(&res->pinned_bytes);
+      const size_t fixed = b_lc0 + b_li0 + b_ls0;
+      if (res->pinned && res->pinned_bytes > fixed + (size_t(64) << 20)) {
+        h_events = (jsb_event*)((uint8_t*)res->pinned + fixed);
+        d_gather = (jsb_event*)ds.buf[BUF_GATHER].p;
+        a.gather_out = d_gather;
+        a.gather_cap = std::min<uint64_t>((res->pinned_bytes - fixed) / sizeof(jsb_event), ds.buf[BUF_GATHER].bytes / sizeof(jsb_event));
+        CUDA_TRY(cudaMalloc(&d_fin, sizeof(uint4) * (size_t)n_local));
+        CUDA_TRY(cudaMalloc(&d_fin_ctr, sizeof(unsigned long long)));
+        CUDA_TRY(cudaMalloc(&d_chunk_prev, sizeof(uint32_t) * n_chunks));
+        CUDA_TRY(cudaMemsetAsync(d_fin, 0xFF, sizeof(uint4) * (size_t)n_local, stream));
+        CUDA_TRY(cudaMemsetAsync(d_fin_ctr, 0, sizeof(unsigned long long), stream));
+        a.fin_list = d_fin; a.fin_ctr = d_fin_ctr; a.chunk_prev = d_chunk_prev;
+      } else {
+        want_stream = false;
+      }
+    }
 
     const char* trace_path = std::getenv("JSB_TRACE");  // debug: per-replicate start/end/SM/iterations, raw u64[4]
     if (trace_path) {
@@ -968,6 +1011,57 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
     }
     res->launches += 1;
     CUDA_TRY(cudaEventRecord(ev1, stream));
+    // ---- streamed outputs ---------------------------------------------------------------------------------------
+    // The kernel time of an ensemble ends in a tail of a few heavy replicates while most SMs and both copy engines
+    // idle, and the event logs are gigabytes.  A replicate that finishes packs its own log into the gather buffer
+    // at rows it draws with one atomic, then publishes itself in fin_list; this thread polls that list on a second
+    // stream and starts the device-to-host copy of every completed run of ranks (contiguous rows), so that when
+    // the kernel ends only the last few logs are left to copy.  When the buffers of the earlier call turn out too
+    // small for this one, everything is gathered and copied after the kernel as before.
+    if (want_stream) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+      CUDA_TRY(cudaHostAlloc(&h_fin, sizeof(uint4) * (size_t)n_local + 64, cudaHostAllocDefault));
+      uint4* h_list = (uint4*)h_fin;
+      unsigned long long* h_ctr = (unsigned long long*)(h_list + n_local);
+      uint64_t processed = 0;
+      bool ok = true;
+      const uint64_t min_batch = (uint64_t)std::max<int64_t>(8, n_local / 128);
+      for (;;) {
+        const cudaError_t q = cudaEventQuery(ev1);
+        if (q != cudaSuccess && q != cudaErrorNotReady) { rc = fail(JSB_ECUDA, "simulation kernel failed: %s", cudaGetErrorString(q)); goto done; }
+        const bool finished = q == cudaSuccess;
+        CUDA_TRY(cudaMemcpyAsync(h_ctr, d_fin_ctr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream2));
+        CUDA_TRY(cudaStreamSynchronize(stream2));
+        const uint64_t cnt = std::min<uint64_t>(*h_ctr >> 40, (uint64_t)n_local);
+        if (cnt > processed && (finished || cnt - processed >= min_batch)) {
+          CUDA_TRY(cudaMemcpyAsync(h_list + processed, d_fin + processed, sizeof(uint4) * (cnt - processed), cudaMemcpyDeviceToHost, stream2));
+          CUDA_TRY(cudaStreamSynchronize(stream2));
+          uint64_t k = processed;
+          while (k < cnt && h_list[k].x != 0xFFFFFFFFu) {  // an entry follows its rank once the log is packed
+            if (h_list[k].x & 0x80000000u) ok = false;      // no room in the buffers of the earlier call
+            ++k;
+          }
+          if (!ok) break;
+          if (k > processed) {
+            const uint64_t e0 = ((uint64_t)h_list[processed].w << 32) | h_list[processed].z;
+            const uint64_t e1 = (((uint64_t)h_list[k - 1].w << 32) | h_list[k - 1].z) + h_list[k - 1].y;
+            if (e1 > e0) CUDA_TRY(cudaMemcpyAsync(h_events + e0, d_gather + e0, sizeof(jsb_event) * (e1 - e0), cudaMemcpyDeviceToHost, stream2));
+            processed = k;
+          }
+        }
+        if (finished && processed == cnt) {
+          if (cnt != (uint64_t)n_local) ok = false;  // every replicate of the call publishes itself
+          break;
+        }
+        if (!finished) std::this_thread::sleep_for(std::chrono::microseconds(300));
+      }
+      CUDA_TRY(cudaStreamSynchronize(stream2));
+      if (ok) {
+        streamed = true;
+        fin_host.assign(h_list, h_list + n_local);
+        ev_total = *h_ctr & ((1ull << 40) - 1ull);
+      }
+    }
     CUDA_TRY(cudaStreamSynchronize(stream));
     {
       float ms = 0.f;
@@ -994,7 +1088,15 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
       CUDA_TRY(cudaMemcpy(res->clones.data(), d_clones, sizeof(jsb_clone) * used, cudaMemcpyDeviceToHost));
       CUDA_TRY(cudaMemcpy(res->clone_off.data(), d_clone_off, sizeof(long long) * n_local, cudaMemcpyDeviceToHost));
     }
-    if (opts->flags & JSB_OUT_EVENTS) {
+    if (streamed) {
+      res->ev_off.assign((size_t)n_local + 1, 0);
+      res->ev_cnt.assign((size_t)n_local, 0);
+      for (int64_t k = 0; k < n_local; ++k) {
+        const uint4 e = fin_host[(size_t)k];
+        res->ev_off[e.x] = ((uint64_t)e.w << 32) | e.z;
+        res->ev_cnt[e.x] = e.y;
+      }
+    } else if (opts->flags & JSB_OUT_EVENTS) {
       uint32_t used_chunks = 0;
       CUDA_TRY(cudaMemcpy(&used_chunks, d_chunk_next, sizeof(uint32_t), cudaMemcpyDeviceToHost));
       used_chunks = std::min(used_chunks, n_chunks);
@@ -1007,27 +1109,32 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
         uint64_t logged = std::min<uint64_t>(res->summaries[i].n_events, (uint64_t)chunks_of[i] * kLogChunk);
         res->ev_off[i + 1] = res->ev_off[i] + logged;
       }
+      res->ev_cnt.resize((size_t)n_local);
+      for (int64_t i = 0; i < n_local; ++i) res->ev_cnt[i] = res->ev_off[i + 1] - res->ev_off[i];
       ev_total = res->ev_off[n_local];
       ev_used_chunks = used_chunks;
     }
     {
-      // one pinned block for every bulk output
+      // one pinned block for every bulk output: [lattice clone | lattice cell | lists | events]
       auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
       const size_t b_ev = up(sizeof(jsb_event) * ev_total);
-      const size_t b_lc = (opts->flags & JSB_OUT_LATTICE) ? up(sizeof(uint16_t) * (size_t)g->nv * n_local) : 0;
-      const size_t b_li = (opts->flags & JSB_OUT_LATTICE) ? up(sizeof(uint32_t) * (size_t)g->nv * n_local) : 0;
-      const size_t b_ls = (opts->flags & JSB_OUT_LISTS) ? up(sizeof(uint32_t) * 2 * (size_t)g->nv * n_local) : 0;
+      const size_t b_lc = b_lc0, b_li = b_li0, b_ls = b_ls0;
       const size_t need = b_ev + b_lc + b_li + b_ls;
-      if (need > 0) {
-        res->pinned = pinned_take(need, &res->pinned_bytes);
-        if (!res->pinned) { rc = fail(JSB_ENOMEM, "cannot pin %llu bytes of host memory for the outputs", (unsigned long long)need); goto done; }
-        uint8_t* base = (uint8_t*)res->pinned;
-        res->events = (jsb_event*)base;
-        res->lat_clone = (uint16_t*)(base + b_ev);
-        res->lat_cell = (uint32_t*)(base + b_ev + b_lc);
-        res->lists = (uint32_t*)(base + b_ev + b_lc + b_li);
+      if (!streamed) {
+        if (res->pinned) { pinned_give(res->pinned, res->pinned_bytes); res->pinned = nullptr; res->pinned_bytes = 0; }
+        if (need > 0) {
+          res->pinned = pinned_take(need, &res->pinned_bytes);
+          if (!res->pinned) { rc = fail(JSB_ENOMEM, "cannot pin %llu bytes of host memory for the outputs", (unsigned long long)need); goto done; }
+        }
       }
-      if (ev_total > 0) {
+      if (res->pinned) {
+        uint8_t* base = (uint8_t*)res->pinned;
+        res->lat_clone = (uint16_t*)base;
+        res->lat_cell = (uint32_t*)(base + b_lc);
+        res->lists = (uint32_t*)(base + b_lc + b_li);
+        res->events = (jsb_event*)(base + b_lc + b_li + b_ls);
+      }
+      if (ev_total > 0 && !streamed) {
         DEV_BUF(d_gather, jsb_event*, BUF_GATHER, sizeof(jsb_event) * ev_total);
         CUDA_TRY(cudaMalloc(&d_ev_off, sizeof(unsigned long long) * (n_local + 1)));
         CUDA_TRY(cudaMemcpyAsync(d_ev_off, res->ev_off.data(), sizeof(unsigned long long) * (n_local + 1), cudaMemcpyHostToDevice, stream));
@@ -1063,6 +1170,9 @@ done:
   // (d_ws, d_log, the chunk tables, d_gather, the lattice / list outputs and d_clones belong to the device cache)
   cudaFree(d_points); cudaFree(d_dpool); cudaFree(d_ipool); cudaFree(d_sum);
   cudaFree(d_counters); cudaFree(d_clone_off); cudaFree(d_chunk_next);
+  cudaFree(d_fin); cudaFree(d_fin_ctr); cudaFree(d_chunk_prev);
+  if (h_fin) cudaFreeHost(h_fin);
+  if (stream2) cudaStreamDestroy(stream2);
   cudaFree(d_ev_off); cudaFree(d_snaps); cudaFree(d_order); cudaFree(d_prio); cudaFree(d_trace);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
@@ -1119,7 +1229,7 @@ int jsb_result_events(jsb_result* r, int64_t i, const jsb_event** p, int64_t* n)
   if (!(r->flags & JSB_OUT_EVENTS)) return fail(JSB_EINVAL, "run did not request JSB_OUT_EVENTS");
   r = part_of(r, i);
   *p = r->events ? r->events + r->ev_off[i] : nullptr;
-  *n = (int64_t)(r->ev_off[i + 1] - r->ev_off[i]);
+  *n = (int64_t)r->ev_cnt[i];
   return JSB_OK;
 }
 
@@ -1193,7 +1303,7 @@ int jsb_result_genealogy(jsb_result* r, int64_t i, const uint32_t* sample_cells,
   if (!(r->flags & JSB_OUT_EVENTS)) return fail(JSB_EINVAL, "run did not request JSB_OUT_EVENTS");
   r = part_of(r, i);
   const jsb_event* ev = r->events ? r->events + r->ev_off[i] : nullptr;
-  const int64_t n = (int64_t)(r->ev_off[i + 1] - r->ev_off[i]);
+  const int64_t n = (int64_t)r->ev_cnt[i];
   // every cell id appears as `cell` in at most one Duplicate/Mutation row (ids are unique), so
   // the backward scan is a pointer chase: mark wanted ids, visit rows from the end.
   std::vector<uint8_t> wanted((size_t)r->summaries[i].next_cell_id + 1, 0);

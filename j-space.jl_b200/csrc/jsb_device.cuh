@@ -109,6 +109,16 @@ struct RunArgs {
   // Suspending pilot: the pilot pass runs with every output on, parks the state of each replicate that reaches
   // `pilot_iters` in `susp` (its slot workspace + registers + shared tables) and finishes the others; the full
   // pass resumes the parked ones.  Same draws, same order: the trajectory does not know it was interrupted.
+  // Streamed outputs: a finished replicate takes (finish rank, first row of its log in the packed output) with one
+  // atomic on fin_ctr = rank << 40 | rows, copies its log chunks to gather_out[first row ...] (walking chunk_prev
+  // back from its last chunk) and then publishes fin_list[rank] = {local index (bit 31: not packed, no room), rows
+  // stored, first row} as a single 16-byte store over a 0xFF-filled array.  The host copies the packed rows of
+  // completed ranks to the host while the kernel is still running (jsb_api.cu).
+  uint4* fin_list;
+  unsigned long long* fin_ctr;
+  jsb_event* gather_out;          // packed output (device); a finished replicate copies its own chunks there
+  unsigned long long gather_cap;  // rows that fit (gather buffer and host block of an earlier call)
+  uint32_t* chunk_prev;           // [n_chunks] previous chunk of the same replicate (kNone for its first)
   uint8_t* susp;            // [n_local][susp_stride]; nullptr: the pilot pass is thrown away (old behaviour)
   uint64_t susp_stride;     // ws_stride + susp_extra_bytes(site_bytes)
   uint32_t* susp_state;     // [n_local] 0 = not started, 1 = parked, 2 = finished in the pilot pass

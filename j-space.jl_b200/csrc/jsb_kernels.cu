@@ -320,6 +320,7 @@ struct Ctx {
 struct Rep {
   double t, theta, lambda, guard;
   uint64_t it, nlog;
+  uint64_t nstored;     // rows in the log pool when it ran out (log_on false); otherwise nlog rows are stored
   uint32_t n, S, next_id, arena_top, cur_chunk, used_w;
   uint32_t dirty_from;  // first clone index whose size changed since the last refold (kNone = clean)
   int bott_id, snap_idx, status;
@@ -340,6 +341,18 @@ __device__ __forceinline__ void occ_clear(uint32_t* occ, uint32_t site) { if (oc
 // ---------------------------------------------------------------------------------------------
 // Event log: 32-byte records in pool chunks, rows in the reference's push! order
 // ---------------------------------------------------------------------------------------------
+// 16-byte streaming copy by one warp (workspace parking, packing a finished log)
+__device__ __forceinline__ void warp_copy16(uint8_t* dst, const uint8_t* src, uint64_t bytes, int lane) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  const uint64_t n = (bytes + 15) >> 4;
+  uint64_t i = (uint64_t)lane;
+  for (; i + 96 < n; i += 128) {
+    const uint4 a = __ldcs(s + i), b = __ldcs(s + i + 32), c = __ldcs(s + i + 64), e = __ldcs(s + i + 96);
+    __stcs(d + i, a); __stcs(d + i + 32, b); __stcs(d + i + 64, c); __stcs(d + i + 96, e);
+  }
+  for (; i < n; i += 32) __stcs(d + i, __ldcs(s + i));
+}
 template <typename T>
 __device__ __noinline__ void log_open_chunk(Ctx<T>& X, Rep& r) {
   uint32_t c = 0;
@@ -348,11 +361,13 @@ __device__ __noinline__ void log_open_chunk(Ctx<T>& X, Rep& r) {
     if (c < X.A->n_chunks) {
       X.A->chunk_owner[c] = (int32_t)X.local_idx;
       X.A->chunk_seq[c] = (uint32_t)(r.nlog / kLogChunk);
+      if (X.A->chunk_prev) X.A->chunk_prev[c] = r.nlog ? r.cur_chunk : kNone;
     }
   }
   c = __shfl_sync(FULL, c, 0);
   if (c >= X.A->n_chunks) {
     r.log_on = false;
+    r.nstored = r.nlog;
     r.status = JSB_ST_LOG_OVERFLOW;
     return;
   }
@@ -391,6 +406,7 @@ __device__ __noinline__ uint32_t log_emit(const RunArgs* A, int64_t local_idx, i
       if (c < A->n_chunks) {
         A->chunk_owner[c] = (int32_t)local_idx;
         A->chunk_seq[c] = (uint32_t)(nlog / kLogChunk);
+        if (A->chunk_prev) A->chunk_prev[c] = nlog ? cur_chunk : kNone;
       }
     }
     c = __shfl_sync(FULL, c, 0);
@@ -418,7 +434,7 @@ __device__ __forceinline__ void log_row(Ctx<T>& X, Rep& r, uint32_t type, uint32
     } else {          // first record of a chunk: claim one from the pool
       const uint32_t c = log_emit(X.A, X.local_idx, X.lane, r.nlog, r.cur_chunk, type, flags, time, cell, parent,
                                   site0 + 1, site2_1, clone, label);
-      if (c == kNone) { r.log_on = false; r.status = JSB_ST_LOG_OVERFLOW; }
+      if (c == kNone) { r.log_on = false; r.nstored = r.nlog; r.status = JSB_ST_LOG_OVERFLOW; }
       else r.cur_chunk = c;
     }
   }
@@ -1714,6 +1730,32 @@ __device__ __noinline__ void write_outputs(Ctx<T>& X, Rep& r) {
     }
   }
   __syncwarp();
+  if (A.fin_list) {
+    unsigned long long stored = 0, old = 0;
+    if (A.flags & JSB_OUT_EVENTS) stored = r.log_on ? r.nlog : r.nstored;
+    if (lane == 0) old = atomicAdd(A.fin_ctr, (1ull << 40) + stored);
+    old = __shfl_sync(FULL, old, 0);
+    const unsigned long long first = old & ((1ull << 40) - 1ull);
+    const uint32_t rank = (uint32_t)(old >> 40);
+    bool packed = stored == 0;
+    if (stored > 0 && A.gather_out && first + stored <= A.gather_cap) {
+      // pack this replicate's chunks (last one first, following chunk_prev) into the output at its rows
+      uint32_t c = r.cur_chunk;
+      for (long long q = (long long)((stored - 1) / kLogChunk); q >= 0; --q) {
+        const unsigned long long done = (unsigned long long)q * kLogChunk;
+        const unsigned long long cnt = stored - done < (unsigned long long)kLogChunk ? stored - done : (unsigned long long)kLogChunk;
+        warp_copy16(reinterpret_cast<uint8_t*>(A.gather_out + first + done),
+                    reinterpret_cast<const uint8_t*>(A.log_pool + (size_t)c * kLogChunk), cnt * sizeof(jsb_event), lane);
+        c = A.chunk_prev[c];
+      }
+      packed = true;
+    }
+    __threadfence();  // everything this replicate wrote is visible before its entry is
+    __syncwarp();
+    if (lane == 0)
+      A.fin_list[rank] = make_uint4((uint32_t)X.local_idx | (packed ? 0u : 0x80000000u), (uint32_t)stored, (uint32_t)first,
+                                    (uint32_t)(first >> 32));
+  }
 }
 
 // Per-lane (t_old, t_curr) of the candidate iterations and everything that can happen besides
@@ -2267,17 +2309,6 @@ __device__ __noinline__ bool run_decoupled(Ctx<T>& Xref, Rep& rref, volatile Hel
 // deterministic), and carries on at iteration it + 1.  Draws are addressed by iteration number, so the
 // trajectory is the one an uninterrupted run produces.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_copy16(uint8_t* dst, const uint8_t* src, uint64_t bytes, int lane) {
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-  uint4* d = reinterpret_cast<uint4*>(dst);
-  const uint64_t n = (bytes + 15) >> 4;
-  uint64_t i = (uint64_t)lane;
-  for (; i + 96 < n; i += 128) {
-    const uint4 a = __ldcs(s + i), b = __ldcs(s + i + 32), c = __ldcs(s + i + 64), e = __ldcs(s + i + 96);
-    __stcs(d + i, a); __stcs(d + i + 32, b); __stcs(d + i + 64, c); __stcs(d + i + 96, e);
-  }
-  for (; i < n; i += 32) __stcs(d + i, __ldcs(s + i));
-}
 template <typename T>
 __device__ __noinline__ void susp_copy(const Ctx<T>& X, uint32_t arena_top, bool save) {
   const RunArgs& A = *X.A;
@@ -2339,7 +2370,7 @@ __device__ __forceinline__ void run_replicate(Ctx<T>& X, volatile HelpMail* M, c
   const DevPoint& P = *X.P;
   const int lane = X.lane;
   Rep r;
-  r.t = 0.0; r.theta = 0.0; r.lambda = 0.0; r.guard = 0.0; r.it = 0; r.nlog = 0; r.cur_chunk = 0;
+  r.t = 0.0; r.theta = 0.0; r.lambda = 0.0; r.guard = 0.0; r.it = 0; r.nlog = 0; r.nstored = 0; r.cur_chunk = 0;
   r.bott_id = P.n_bott > 0 ? 1 : 0;  // :668-672
   r.snap_idx = 0;
   r.status = JSB_ST_OK;

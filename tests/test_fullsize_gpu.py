@@ -180,3 +180,32 @@ def test_ensemble_statistics_ks(jsb, oracle):
         if r.summary["n_alive"] > 0:
             frac_cpu.append(r.clones["count"].max() / r.summary["n_alive"])
     assert stats.ks_2samp(frac_gpu, frac_cpu).pvalue > 0.01
+
+
+def test_streamed_outputs_equal_outputs_gathered_after_the_kernel(jsb, monkeypatch):
+    # From the second call on, the logs of finished replicates are packed and copied to the host while the kernel is
+    # still running (jsb_api.cu, "streamed outputs"): rows land in finish order in the host block, the accessors must
+    # return exactly what the gather-after-the-kernel path returns, for every replicate.
+    from jspace_b200 import _lib as L
+    g = jsb.Graph.lattice(100, 100, 2)
+    p = jsb.Point(**dict(DEFAULT, Tf=120.0, t_bottleneck=[50.0], ratio_bottleneck=[0.8], t_snapshot=[30.0]))
+    flags = L.OUT_EVENTS | L.OUT_LATTICE | L.OUT_LISTS
+
+    def run(seed):
+        return jsb.run_ensemble(g, p, 1600, seed=seed, flags=flags, log_pool_bytes=2 << 30)
+    run(7).close()                      # leaves a pinned block and a gather buffer behind
+    a = run(8)                          # streamed
+    monkeypatch.setenv("JSB_NO_STREAM_OUT", "1")
+    b = run(8)                          # gathered and copied after the kernel
+    assert a.launches < b.launches, "the second call was expected to stream its outputs (no gather launch)"
+    assert a.summaries.tobytes() == b.summaries.tobytes()
+    assert int(a.summaries["n_events"].sum()) > 1_000_000
+    for i in range(a.count):
+        assert a.events(i).tobytes() == b.events(i).tobytes(), i
+        la, lb = a.lattice(i), b.lattice(i)
+        assert la[0].tobytes() == lb[0].tobytes() and la[1].tobytes() == lb[1].tobytes(), i
+    for i in (0, 5, 1599):
+        assert a.list(i, 0).tobytes() == b.list(i, 0).tobytes() and a.clones(i).tobytes() == b.clones(i).tobytes()
+        assert a.snapshots(i).tobytes() == b.snapshots(i).tobytes()
+    a.close()
+    b.close()
