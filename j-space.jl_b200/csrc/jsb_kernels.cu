@@ -2359,7 +2359,8 @@ __device__ __noinline__ void susp_restore(Ctx<T>& X, Rep& r) {
   }
   r.dirty_from = 0;
   r.exact_valid = false;
-  r.status = JSB_ST_OK;
+  // the pilot depth is not an outcome; a log pool that ran out during the pilot pass is
+  r.status = ((A.flags & JSB_OUT_EVENTS) && !r.log_on) ? JSB_ST_LOG_OVERFLOW : JSB_ST_OK;
   X.search_top = 2;
   __syncwarp();
 }

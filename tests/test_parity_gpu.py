@@ -277,3 +277,37 @@ def test_genealogy_of_sampled_cells(jsb, oracle):
     assert got == rows and len(rows) >= len(sample)
     assert wanted == {1}  # every sampled lineage coalesces in the seed cell
     res.close()
+
+
+def test_log_pool_exhaustion_keeps_a_prefix_of_the_log(jsb, monkeypatch):
+    # An event-log pool that is too small: a replicate that cannot claim another chunk keeps the rows it has (whole
+    # chunks of 1024), carries on without a log and reports JSB_ST_LOG_OVERFLOW — also when it was parked by the pilot
+    # pass and resumed, and also when the outputs are streamed (second call).  Everything else must equal the run with
+    # a pool that is large enough.
+    from jspace_b200 import _lib as L
+    monkeypatch.setenv("JSB_DEBUG_GRID", "3")
+    monkeypatch.setenv("JSB_PILOT_ITERS", "2000")
+    g = jsb.Graph.lattice(64, 64, 2)
+    p = jsb.Point(**dict(DEFAULT, Tf=90.0, rate_birth=0.5))
+    flags = L.OUT_EVENTS | L.OUT_LATTICE
+    full = jsb.run_ensemble(g, p, 40, seed=3, flags=flags, warps_per_sm=2, log_pool_bytes=256 << 20)
+    assert np.all(full.summaries["status"] == L.ST_OK) and int(full.summaries["n_events"].max()) > 4096
+    needed = int(np.ceil(full.summaries["n_events"] / 1024.0).sum())  # chunks of 1024 rows
+    for attempt in range(2):  # the second call finds a pinned block and a gather buffer: streamed
+        small = jsb.run_ensemble(g, p, 40, seed=3, flags=flags, warps_per_sm=2, log_pool_bytes=(needed * 2 // 3) * 1024 * 32)
+        st = small.summaries["status"]
+        assert int((st == L.ST_LOG_OVERFLOW).sum()) >= 2 and int((st == L.ST_OK).sum()) >= 2, st
+        a, b = small.summaries.copy(), full.summaries.copy()
+        a["status"] = 0
+        b["status"] = 0
+        assert a.tobytes() == b.tobytes()  # the trajectories themselves are untouched
+        for i in range(40):
+            es, ef = small.events(i), full.events(i)
+            if st[i] == L.ST_LOG_OVERFLOW:
+                assert len(es) < len(ef) and len(es) % 1024 == 0
+            else:
+                assert len(es) == len(ef)
+            assert es.tobytes() == ef[:len(es)].tobytes(), i
+            assert small.lattice(i)[0].tobytes() == full.lattice(i)[0].tobytes()
+        small.close()
+    full.close()
