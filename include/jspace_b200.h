@@ -76,6 +76,9 @@ extern "C" {
 #define JSB_OUT_EVENTS 0x1u  /* keep the per-replicate event log (`df`)                   */
 #define JSB_OUT_LATTICE 0x2u /* keep the final lattice (clone id + cell id per site)      */
 #define JSB_OUT_LISTS 0x4u   /* keep the final ordered cs_alive / ca_subpop lists          */
+#define JSB_OUT_SERIES 0x8u  /* keep the per-effective-event series (list_len_node_occ, CA_Alive_TOT;
+                              * src/J_Space.jl:656-658,740-741,757-758,807-808,835-836) without shipping
+                              * the event log to the host: the log is reduced on the device           */
 /* ---- simulation mode (jsb_run_opts.flags) ------------------------------------------------
  * JSB_MODE_REJECTION_FREE: same stochastic law, different algorithm.  Null
  * events are not simulated: a per-site propensity tree selects only state-changing events and
@@ -110,6 +113,18 @@ typedef struct jsb_event {
   uint8_t flags;    /* JSB_EVF_*                                                          */
   uint16_t pad;
 } jsb_event; /* 32 bytes */
+
+/* One push to list_len_node_occ / CA_Alive_TOT (one effective event).  The reference pushes n_cs_alive and
+ * length.(ca_subpop); a row holds n_cs_alive and the one or two list lengths that changed, so that the
+ * caller rebuilds the per-clone counts by running sums.  An excision that removes k > 1 cells is ONE push:
+ * it is written as k rows, all but the last with JSB_SERIES_MORE set in n_alive.                       */
+#define JSB_SERIES_MORE 0x80000000u
+typedef struct jsb_series_row {
+  uint32_t n_alive; /* n_cs_alive after the row (low 31 bits)                                        */
+  uint16_t gain;    /* clone (1-based) whose list grew by one cell, 0 = none; the first time an index
+                       appears it is a new clone of one cell (Mutation)                               */
+  uint16_t loss;    /* clone whose list lost one cell, 0 = none                                       */
+} jsb_series_row; /* 8 bytes */
 
 /* ---- clone table: set_mut_pop + α of the 7-tuple (src/J_Space.jl:841) ------------------ */
 typedef struct jsb_clone {
@@ -263,6 +278,11 @@ int jsb_result_lattice(const jsb_result* r, int64_t i, const uint16_t** clone,
  * vertex numbers.                                                                         */
 int jsb_result_list(jsb_result* r, int64_t i, int32_t list, const uint32_t** p, int64_t* n);
 int jsb_result_snapshots(const jsb_result* r, int64_t i, const jsb_snapshot** p, int32_t* n);
+/* JSB_OUT_SERIES: the rows of replicate i (the initial entry of list_len_node_occ, src/J_Space.jl:658, is the
+ * number of starting cells and is not a row), and for every snapshot the number of rows before it
+ * (CA_Alive_TOT gets an extra row there, :712).                                                       */
+int jsb_result_series(const jsb_result* r, int64_t i, const jsb_series_row** p, int64_t* n,
+                      const int64_t** rows_before_snapshot, int32_t* n_snapshots);
 /* Ensemble histograms over this shard (fixed bins, uint64 counts) for sweep point `point`:
  * kind 0 = final n_alive (bins of width nv/64), kind 1 = n_clones (bins 0..63+),
  * kind 2 = log2(n_iterations).  64 bins each; meant to be summed over ranks with NCCL.     */

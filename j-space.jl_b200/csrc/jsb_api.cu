@@ -415,6 +415,9 @@ struct jsb_result {
   uint32_t* lists = nullptr;
   std::vector<jsb_snapshot> snaps;
   std::vector<int32_t> snap_count;
+  std::vector<jsb_series_row> series;   // JSB_OUT_SERIES: rows of every replicate, replicate-major
+  std::vector<uint64_t> ser_off;        // n_local + 1
+  std::vector<int64_t> ser_snap;        // [n_local][max_snap] rows before every snapshot
   double kernel_ms = 0.0;
   int64_t launches = 0;
   // a multi-device call: one result per device shard (this object then only holds the merged summaries)
@@ -456,6 +459,56 @@ __global__ void gather_log_kernel(const jsb_event* __restrict__ pool, const int3
     uint4* dst = reinterpret_cast<uint4*>(out + first);
     for (unsigned long long i = threadIdx.x; i < cnt * 2; i += blockDim.x) dst[i] = src[i];
   }
+}
+
+// JSB_OUT_SERIES: the packed log of one replicate reduced to its series rows (include/jspace_b200.h), one thread
+// per replicate; WRITE = false only counts.  Rows flagged JSB_EVF_GROUP_START open one push: a Death row takes a
+// cell from its clone, the (Duplicate | Mutation, Duplicate) pair that closes a birth gives one to the clone of its
+// first row, a Migration changes nothing; excision Deaths are one push written as one row per cell.
+template <bool WRITE>
+__global__ void series_kernel(const jsb_event* __restrict__ ev, const unsigned long long* __restrict__ ev_off,
+                              const unsigned long long* __restrict__ ev_cnt, const uint32_t* __restrict__ n0,
+                              const jsb_snapshot* __restrict__ snaps, int max_snap, long long n_local,
+                              unsigned long long* __restrict__ ser_cnt, const unsigned long long* __restrict__ ser_off,
+                              jsb_series_row* __restrict__ out, long long* __restrict__ snap_rows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_local) return;
+  const jsb_event* e = ev + ev_off[i];
+  const unsigned long long m = ev_cnt[i];
+  jsb_series_row* o = WRITE ? out + ser_off[i] : nullptr;
+  unsigned long long rows = 0;
+  uint32_t n = n0[i];
+  int si = 0;
+  unsigned long long k = 0;
+  while (k < m) {
+    // the group [k, ge)
+    unsigned long long ge = k + 1;
+    while (ge < m && !(e[ge].flags & JSB_EVF_GROUP_START)) ++ge;
+    if (WRITE && snaps)
+      while (si < max_snap && snaps[(size_t)i * max_snap + si].index != 0xFFFFFFFFu &&
+             snaps[(size_t)i * max_snap + si].n_events_before <= k) snap_rows[(size_t)i * max_snap + si++] = (long long)rows;
+    if (e[k].flags & JSB_EVF_EXCISION) {
+      for (unsigned long long q = k; q < ge; ++q) {
+        --n;
+        if (WRITE) { jsb_series_row r; r.n_alive = n | (q + 1 < ge ? JSB_SERIES_MORE : 0u); r.gain = 0; r.loss = e[q].clone; o[rows] = r; }
+        ++rows;
+      }
+    } else {
+      uint16_t gain = 0, loss = 0;
+      for (unsigned long long q = k; q < ge; ++q)
+        if (e[q].type == JSB_EV_DEATH) { loss = e[q].clone; --n; }
+      if (ge - k >= 2 && e[ge - 1].type == JSB_EV_DUPLICATE && (e[ge - 2].type == JSB_EV_DUPLICATE || e[ge - 2].type == JSB_EV_MUTATION)) {
+        gain = e[ge - 2].clone;
+        ++n;
+      }
+      if (WRITE) { jsb_series_row r; r.n_alive = n; r.gain = gain; r.loss = loss; o[rows] = r; }
+      ++rows;
+    }
+    k = ge;
+  }
+  if (WRITE && snaps)
+    while (si < max_snap && snaps[(size_t)i * max_snap + si].index != 0xFFFFFFFFu) snap_rows[(size_t)i * max_snap + si++] = (long long)rows;
+  if (!WRITE) ser_cnt[i] = rows;
 }
 
 }  // namespace jsb
@@ -704,6 +757,8 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
   long long* d_clone_off = nullptr;
   jsb_event *d_log = nullptr, *d_gather = nullptr;
   uint32_t* d_chunk_next = nullptr;
+  unsigned long long* d_ser_meta = nullptr;  // JSB_OUT_SERIES scratch
+  jsb_series_row* d_series = nullptr;
   uint4* d_fin = nullptr;               // [n_local] fin_list (streamed outputs)
   uint32_t* d_chunk_prev = nullptr;
   unsigned long long* d_fin_ctr = nullptr;
@@ -863,7 +918,10 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
     DEV_BUF(d_clones, jsb_clone*, BUF_CLONES, sizeof(jsb_clone) * clone_cap);
     CUDA_TRY(cudaMalloc(&d_clone_off, sizeof(long long) * n_local));
     uint32_t n_chunks = 0;
-    if (opts->flags & JSB_OUT_EVENTS) {
+    const bool ret_series = (opts->flags & JSB_OUT_SERIES) != 0 && !fast_mode;
+    const bool ret_events = (opts->flags & JSB_OUT_EVENTS) != 0;
+    const bool log_needed = ret_events || ret_series;  // the series is a reduction of the log, done on the device
+    if (log_needed) {
       size_t free_b = 0, total_b = 0;
       CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
       uint64_t want = opts->log_pool_bytes ? opts->log_pool_bytes : (1ull << 30);
@@ -900,7 +958,7 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
     }
     a.points = d_points; a.dpool = d_dpool; a.ipool = d_ipool;
     a.seed_cand = gd.d_cand; a.n_cand = gd.d_ncand;
-    a.flags = opts->flags; a.seed = opts->seed; a.g_begin = g_begin; a.n_local = n_local; a.reps_per_point = reps_per_point;
+    a.flags = opts->flags | (log_needed ? JSB_OUT_EVENTS : 0u); a.seed = opts->seed; a.g_begin = g_begin; a.n_local = n_local; a.reps_per_point = reps_per_point;
     a.ws = d_ws; a.ws_stride = L.total; a.arena_cap = arena_cap; a.site_bytes = site_bytes; a.L = L;
     a.summaries = d_sum; a.clone_pool = d_clones; a.clone_pool_cap = clone_cap; a.clone_pool_next = d_counters + 1;
     a.clone_off = d_clone_off;
@@ -913,7 +971,7 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
     const size_t b_lc0 = (opts->flags & JSB_OUT_LATTICE) ? ((sizeof(uint16_t) * (size_t)g->nv * n_local + 255) & ~size_t(255)) : 0;
     const size_t b_li0 = (opts->flags & JSB_OUT_LATTICE) ? ((sizeof(uint32_t) * (size_t)g->nv * n_local + 255) & ~size_t(255)) : 0;
     const size_t b_ls0 = (opts->flags & JSB_OUT_LISTS) ? ((sizeof(uint32_t) * 2 * (size_t)g->nv * n_local + 255) & ~size_t(255)) : 0;
-    bool want_stream = (opts->flags & JSB_OUT_EVENTS) && !fast_mode && !std::getenv("JSB_NO_STREAM_OUT") && ds.buf[BUF_GATHER].p;
+    bool want_stream = ret_events && !fast_mode && !std::getenv("JSB_NO_STREAM_OUT") && ds.buf[BUF_GATHER].p;
     jsb_event* h_events = nullptr;
     if (want_stream) {
       res->pinned = pinned_take_cached(&res->pinned_bytes);
@@ -1096,7 +1154,7 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
         res->ev_off[e.x] = ((uint64_t)e.w << 32) | e.z;
         res->ev_cnt[e.x] = e.y;
       }
-    } else if (opts->flags & JSB_OUT_EVENTS) {
+    } else if (log_needed) {
       uint32_t used_chunks = 0;
       CUDA_TRY(cudaMemcpy(&used_chunks, d_chunk_next, sizeof(uint32_t), cudaMemcpyDeviceToHost));
       used_chunks = std::min(used_chunks, n_chunks);
@@ -1117,7 +1175,7 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
     {
       // one pinned block for every bulk output: [lattice clone | lattice cell | lists | events]
       auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
-      const size_t b_ev = up(sizeof(jsb_event) * ev_total);
+      const size_t b_ev = ret_events ? up(sizeof(jsb_event) * ev_total) : 0;
       const size_t b_lc = b_lc0, b_li = b_li0, b_ls = b_ls0;
       const size_t need = b_ev + b_lc + b_li + b_ls;
       if (!streamed) {
@@ -1132,7 +1190,7 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
         res->lat_clone = (uint16_t*)base;
         res->lat_cell = (uint32_t*)(base + b_lc);
         res->lists = (uint32_t*)(base + b_lc + b_li);
-        res->events = (jsb_event*)(base + b_lc + b_li + b_ls);
+        res->events = ret_events ? (jsb_event*)(base + b_lc + b_li + b_ls) : nullptr;
       }
       if (ev_total > 0 && !streamed) {
         DEV_BUF(d_gather, jsb_event*, BUF_GATHER, sizeof(jsb_event) * ev_total);
@@ -1142,7 +1200,46 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
         gather_log_kernel<<<gblocks, 256, 0, stream>>>(d_log, d_chunk_owner, d_chunk_seq, d_ev_off, ev_used_chunks, d_gather);
         CUDA_TRY(cudaGetLastError());
         res->launches += 1;
-        CUDA_TRY(cudaMemcpyAsync(res->events, d_gather, sizeof(jsb_event) * ev_total, cudaMemcpyDeviceToHost, stream));
+        if (ret_events) CUDA_TRY(cudaMemcpyAsync(res->events, d_gather, sizeof(jsb_event) * ev_total, cudaMemcpyDeviceToHost, stream));
+      }
+      if (ret_series) {
+        // the packed log (d_gather: streamed or gathered just now) reduced to series rows on the device
+        const size_t nl = (size_t)n_local;
+        std::vector<uint32_t> n0(nl);
+        for (size_t i = 0; i < nl; ++i) {
+          const int32_t ns = points[(g_begin + (int64_t)i) / reps_per_point].n_start_cells;
+          n0[i] = (uint32_t)(ns < 0 ? 0 : ns);
+        }
+        CUDA_TRY(cudaMalloc(&d_ser_meta, sizeof(unsigned long long) * 4 * nl + sizeof(uint32_t) * nl + sizeof(long long) * nl * (size_t)std::max(1, max_snap)));
+        unsigned long long* d_off = d_ser_meta;
+        unsigned long long* d_cnt = d_off + nl;
+        unsigned long long* d_scnt = d_cnt + nl;
+        unsigned long long* d_soff = d_scnt + nl;
+        long long* d_snap_rows = reinterpret_cast<long long*>(d_soff + nl);
+        uint32_t* d_n0 = reinterpret_cast<uint32_t*>(d_snap_rows + nl * (size_t)std::max(1, max_snap));
+        CUDA_TRY(cudaMemcpyAsync(d_off, res->ev_off.data(), sizeof(unsigned long long) * nl, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(d_cnt, res->ev_cnt.data(), sizeof(unsigned long long) * nl, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(d_n0, n0.data(), sizeof(uint32_t) * nl, cudaMemcpyHostToDevice, stream));
+        const int sblocks = (int)((nl + 63) / 64);
+        const jsb_event* d_packed = ev_total > 0 ? d_gather : nullptr;
+        series_kernel<false><<<sblocks, 64, 0, stream>>>(d_packed, d_off, d_cnt, d_n0, nullptr, 0, n_local, d_scnt, nullptr, nullptr, nullptr);
+        CUDA_TRY(cudaGetLastError());
+        std::vector<unsigned long long> scnt(nl);
+        CUDA_TRY(cudaMemcpyAsync(scnt.data(), d_scnt, sizeof(unsigned long long) * nl, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        res->ser_off.assign(nl + 1, 0);
+        for (size_t i = 0; i < nl; ++i) res->ser_off[i + 1] = res->ser_off[i] + scnt[i];
+        const uint64_t ser_total = res->ser_off[nl];
+        res->series.resize((size_t)ser_total);
+        res->ser_snap.assign(nl * (size_t)std::max(1, max_snap), 0);
+        CUDA_TRY(cudaMalloc(&d_series, sizeof(jsb_series_row) * std::max<uint64_t>(ser_total, 1)));
+        CUDA_TRY(cudaMemcpyAsync(d_soff, res->ser_off.data(), sizeof(unsigned long long) * nl, cudaMemcpyHostToDevice, stream));
+        series_kernel<true><<<sblocks, 64, 0, stream>>>(d_packed, d_off, d_cnt, d_n0, max_snap > 0 ? d_snaps : nullptr, max_snap, n_local, nullptr,
+                                                        d_soff, d_series, d_snap_rows);
+        CUDA_TRY(cudaGetLastError());
+        res->launches += 2;
+        if (ser_total) CUDA_TRY(cudaMemcpyAsync(res->series.data(), d_series, sizeof(jsb_series_row) * ser_total, cudaMemcpyDeviceToHost, stream));
+        if (max_snap > 0) CUDA_TRY(cudaMemcpyAsync(res->ser_snap.data(), d_snap_rows, sizeof(long long) * nl * (size_t)max_snap, cudaMemcpyDeviceToHost, stream));
       }
       if (opts->flags & JSB_OUT_LATTICE) {
         CUDA_TRY(cudaMemcpyAsync(res->lat_clone, d_out_clone, sizeof(uint16_t) * (size_t)g->nv * n_local, cudaMemcpyDeviceToHost, stream));
@@ -1170,7 +1267,7 @@ done:
   // (d_ws, d_log, the chunk tables, d_gather, the lattice / list outputs and d_clones belong to the device cache)
   cudaFree(d_points); cudaFree(d_dpool); cudaFree(d_ipool); cudaFree(d_sum);
   cudaFree(d_counters); cudaFree(d_clone_off); cudaFree(d_chunk_next);
-  cudaFree(d_fin); cudaFree(d_fin_ctr); cudaFree(d_chunk_prev);
+  cudaFree(d_fin); cudaFree(d_fin_ctr); cudaFree(d_chunk_prev); cudaFree(d_ser_meta); cudaFree(d_series);
   if (h_fin) cudaFreeHost(h_fin);
   if (stream2) cudaStreamDestroy(stream2);
   cudaFree(d_ev_off); cudaFree(d_snaps); cudaFree(d_order); cudaFree(d_prio); cudaFree(d_trace);
@@ -1269,6 +1366,22 @@ int jsb_result_snapshots(const jsb_result* r, int64_t i, const jsb_snapshot** p,
   if (r->max_snap == 0) { *p = nullptr; *n = 0; return JSB_OK; }
   *p = r->snaps.data() + (size_t)i * r->max_snap;
   *n = r->snap_count[i];
+  return JSB_OK;
+}
+
+int jsb_result_series(const jsb_result* r, int64_t i, const jsb_series_row** p, int64_t* n,
+                      const int64_t** rows_before_snapshot, int32_t* n_snapshots) {
+  CHECK_INDEX(r, i);
+  if (!p || !n) return fail(JSB_EINVAL, "null argument");
+  if (!(r->flags & JSB_OUT_SERIES)) return fail(JSB_EINVAL, "run did not request JSB_OUT_SERIES");
+  r = part_of(r, i);
+  if (r->ser_off.empty()) return fail(JSB_EINVAL, "the rejection-free mode keeps no series");
+  *p = r->series.data() + r->ser_off[i];
+  *n = (int64_t)(r->ser_off[i + 1] - r->ser_off[i]);
+  if (rows_before_snapshot && n_snapshots) {
+    *rows_before_snapshot = r->max_snap ? r->ser_snap.data() + (size_t)i * r->max_snap : nullptr;
+    *n_snapshots = r->max_snap ? r->snap_count[i] : 0;
+  }
   return JSB_OK;
 }
 

@@ -27,7 +27,8 @@ QUIRK_DEBUG_EXACT_CLASSES = 0x200
 QUIRK_DEBUG_WIDE_GUARD = 0x400
 QUIRK_DEBUG_VERIFY_TREE = 0x800
 QUIRK_DEBUG_DECOUPLE = 0x1000
-OUT_EVENTS, OUT_LATTICE, OUT_LISTS = 0x1, 0x2, 0x4
+OUT_EVENTS, OUT_LATTICE, OUT_LISTS, OUT_SERIES = 0x1, 0x2, 0x4, 0x8
+SERIES_MORE = 0x80000000
 MODE_REJECTION_FREE = 0x100
 EV_DUPLICATE, EV_MUTATION, EV_DEATH, EV_MIGRATION = 0, 1, 2, 3
 EVF_GROUP_START, EVF_DISPLACED, EVF_EXCISION = 0x1, 0x2, 0x4
@@ -46,7 +47,8 @@ SNAPSHOT_DTYPE = np.dtype([("time", "<f8"), ("iteration", "<u8"), ("n_events_bef
                            ("n_alive", "<u4"), ("index", "<u4")])
 RELATION_DTYPE = np.dtype([("time", "<f8"), ("father", "<u4"), ("child", "<u4"),
                            ("subpop_child", "<u2"), ("type", "u1"), ("pad", "u1", (5,))])
-assert EVENT_DTYPE.itemsize == 32 and CLONE_DTYPE.itemsize == 16
+SERIES_DTYPE = np.dtype([("n_alive", "<u4"), ("gain", "<u2"), ("loss", "<u2")])
+assert EVENT_DTYPE.itemsize == 32 and CLONE_DTYPE.itemsize == 16 and SERIES_DTYPE.itemsize == 8
 assert SUMMARY_DTYPE.itemsize == 64 and SNAPSHOT_DTYPE.itemsize == 32
 assert RELATION_DTYPE.itemsize == 24
 
@@ -107,6 +109,7 @@ SIGNATURES = {
     "jsb_result_lattice": (C.c_int, [_VP, C.c_int64, _PVP, _PVP]),
     "jsb_result_list": (C.c_int, [_VP, C.c_int64, C.c_int32, _PVP, C.POINTER(C.c_int64)]),
     "jsb_result_snapshots": (C.c_int, [_VP, C.c_int64, _PVP, C.POINTER(C.c_int32)]),
+    "jsb_result_series": (C.c_int, [_VP, C.c_int64, _PVP, C.POINTER(C.c_int64), _PVP, C.POINTER(C.c_int32)]),
     "jsb_result_histogram": (C.c_int, [_VP, C.c_int64, C.c_int, _VP]),
     "jsb_result_free": (None, [_VP]),
     "jsb_result_genealogy": (C.c_int, [_VP, C.c_int64, _VP, C.c_int64, _PVP, C.POINTER(C.c_int64)]),

@@ -197,6 +197,48 @@ class EnsembleResult:
         L.check(L.lib().jsb_result_snapshots(self._h, i, C.byref(p), C.byref(n)))
         return L.view(p.value, n.value, L.SNAPSHOT_DTYPE)
 
+    def series_rows(self, i: int):
+        """JSB_OUT_SERIES: (rows, rows_before_snapshot) of replicate i — one row per push to list_len_node_occ /
+        CA_Alive_TOT (an excision removing k cells: k rows, all but the last with SERIES_MORE)."""
+        p, n, ps, ns = C.c_void_p(), C.c_int64(), C.c_void_p(), C.c_int32()
+        L.check(L.lib().jsb_result_series(self._h, i, C.byref(p), C.byref(n), C.byref(ps), C.byref(ns)))
+        snaps = L.view(ps.value, ns.value, np.int64) if ns.value else np.zeros(0, dtype=np.int64)
+        return L.view(p.value, n.value, L.SERIES_DTYPE), snaps
+
+    def series(self, i: int, n0: int = 1):
+        """(list_len_node_occ, CA_Alive_TOT) of replicate i as the reference builds them (src/J_Space.jl:656-658,
+        712, 740-741, 757-758, 807-808, 835-836), from the device-side series; n0 = number of starting cells."""
+        rows, snaps = self.series_rows(i)
+        n_occ = [int(n0)]
+        counts = [int(n0)] if n0 else []
+        ca_tot = []
+        snap_at = sorted(int(x) for x in snaps)
+        si = 0
+        k = 0
+        while k < len(rows):
+            while si < len(snap_at) and snap_at[si] <= k:
+                ca_tot.append(list(counts))
+                si += 1
+            while True:  # one push: the rows up to the first one without SERIES_MORE
+                r = rows[k]
+                if r["loss"]:
+                    counts[int(r["loss"]) - 1] -= 1
+                if r["gain"]:
+                    g = int(r["gain"])
+                    if g > len(counts):
+                        counts.append(1)
+                    else:
+                        counts[g - 1] += 1
+                k += 1
+                if not (int(r["n_alive"]) & L.SERIES_MORE):
+                    break
+            n_occ.append(int(r["n_alive"]) & 0x7FFFFFFF)
+            ca_tot.append(list(counts))
+        while si < len(snap_at):
+            ca_tot.append(list(counts))
+            si += 1
+        return n_occ, ca_tot
+
     def histogram(self, point: int, kind: int) -> np.ndarray:
         out = np.zeros(64, dtype=np.uint64)
         L.check(L.lib().jsb_result_histogram(self._h, point, kind, out.ctypes.data))

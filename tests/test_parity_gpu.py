@@ -311,3 +311,42 @@ def test_log_pool_exhaustion_keeps_a_prefix_of_the_log(jsb, monkeypatch):
             assert small.lattice(i)[0].tobytes() == full.lattice(i)[0].tobytes()
         small.close()
     full.close()
+
+
+@pytest.mark.parametrize("rule,method", [("contact", 1), ("voter", 1), ("hvoter", 2)])
+def test_device_side_series_equals_oracle_series_and_log_replay(jsb, oracle, rule, method):
+    # JSB_OUT_SERIES: list_len_node_occ / CA_Alive_TOT reduced from the log on the device (no log on the host):
+    # against the oracle's own series, and against the host replay of the log of the same run
+    from jspace_b200 import _lib as L
+    from jspace_b200.api import replay_series
+    from parity import make_graphs
+    p = dict(DEFAULT, Tf=70.0, rule=rule, t_bottleneck=[25.0, 45.0], ratio_bottleneck=[0.6, 0.3], t_snapshot=[10.0, 30.0])
+    if method == 2:
+        p = dict(method=2, Tf=70.0, rate_death=0.02, rate_migration=0.01, mu_driver=0.05, rule=rule, tree_edges=TREE_EDGES,
+                 node_rate=TREE_RATES, root_node=0, root_rate=0.3, t_bottleneck=[30.0], ratio_bottleneck=[0.5],
+                 t_snapshot=[20.0])
+    gj, go = make_graphs(jsb, oracle, ("lattice", 2, 30, 30))
+    only_series = jsb.run_ensemble(gj, jsb.Point(**p), 24, seed=11, flags=L.OUT_SERIES)
+    both = jsb.run_ensemble(gj, jsb.Point(**p), 24, seed=11, flags=L.OUT_SERIES | L.OUT_EVENTS)
+    assert only_series.summaries.tobytes() == both.summaries.tobytes()
+    with pytest.raises(L.JSpaceError):
+        only_series.events(0)
+    exact = 0
+    for i in range(24):
+        o = oracle.Run(go, oracle.make_params(**p), 11, i)
+        n_occ, ca_tot = only_series.series(i)
+        # (an excision that removes no cell pushes in the reference but writes no log row, DESIGN.md 6: the
+        # device-side series then has one entry less than n_effective + 1)
+        assert len(n_occ) - 1 <= int(only_series.summaries["n_effective"][i])
+        if len(n_occ) - 1 == int(only_series.summaries["n_effective"][i]):
+            assert n_occ == o.series.tolist(), i
+            exact += 1
+        assert only_series.series_rows(i)[0].tobytes() == both.series_rows(i)[0].tobytes()
+        ev = both.events(i)
+        n_occ2, ca_tot2 = replay_series(ev, 1, [int(s["n_events_before"]) for s in both.snapshots(i)])
+        assert ca_tot == ca_tot2 and n_occ == n_occ2
+        if len(ca_tot):
+            assert ca_tot[-1] == o.clones["count"].tolist()
+    assert exact >= 20
+    only_series.close()
+    both.close()
