@@ -42,7 +42,7 @@ static unsigned long long run_method1(jsb_graph* g, unsigned long long seed, lon
   jsb_run_opts o;
   memset(&o, 0, sizeof o);
   o.size = (uint32_t)sizeof o;
-  o.flags = JSB_OUT_EVENTS | JSB_OUT_LATTICE;
+  o.flags = JSB_OUT_EVENTS | JSB_OUT_LATTICE | JSB_OUT_SERIES;
   o.seed = seed;
   o.g_begin = stream; o.g_end = stream + 1;   /* the wrapper's stream counter */
   jsb_result* res = NULL;
@@ -67,6 +67,12 @@ static unsigned long long run_method1(jsb_graph* g, unsigned long long seed, lon
   for (int64_t v = 0; v < nv; ++v) { alive += lat[v] != 0; h = mix(h, ids[v]); }
   if (alive != sum->n_alive) { fprintf(stderr, "lattice/summary mismatch\n"); exit(1); }
   for (int32_t i = 0; i < nsn; ++i) h = mix(h, sn[i].n_events_before);
+  /* n_cell_alive / CA_subpop series (what Start.jl:105-116 writes), reduced on the device */
+  const jsb_series_row* ser = NULL; int64_t nser = 0; const int64_t* before = NULL; int32_t nsn2 = 0;
+  CHECK(jsb_result_series(res, 0, &ser, &nser, &before, &nsn2));
+  if (nsn2 != nsn) { fprintf(stderr, "series/snapshot count mismatch\n"); exit(1); }
+  if (nser > 0 && (ser[nser - 1].n_alive & ~JSB_SERIES_MORE) != sum->n_alive) { fprintf(stderr, "series does not end at n_alive\n"); exit(1); }
+  for (int64_t i = 0; i < nser; ++i) { h = mix(h, ser[i].n_alive); h = mix(h, ((unsigned long long)ser[i].gain << 16) | ser[i].loss); }
   /* genealogy of the alive cells (what sampling_phylogentic_relation needs) */
   uint32_t* sample = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(alive > 0 ? alive : 1));
   int64_t ns = 0;
