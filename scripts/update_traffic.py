@@ -3,8 +3,8 @@
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,... --csv --log-file X bench.py ...).
 usage: update_traffic.py launches.csv WORKLOAD REPS  (run from the repo root, on the build the list was taken with)
 
-Takes the LONGEST ssa_kernel launch of the list (the main launch of a step; the pilot launch is the short
-one), adds its DRAM bytes read + written, and records the value under "WORKLOAD:REPS" together with the hash of
+Takes the LAST main ssa_kernel launch of the list (the timed step of `--steps 1 --warmup 1`; main launches are the
+long ones, the pilot launches the short ones), adds its DRAM bytes read + written, and records the value under "WORKLOAD:REPS" together with the hash of
 the kernel sources, so that bench.py only quotes it for the build it was measured on."""
 import csv
 import json
@@ -35,7 +35,9 @@ def main():
     def dur(m):
         v, u = m["gpu__time_duration.sum"]
         return v * tscale[u]
-    main_id = max(per, key=lambda k: dur(per[k]))
+    longest = max(dur(m) for m in per.values())
+    mains = [k for k in per if dur(per[k]) > 0.5 * longest]      # main launches (the pilot launches are the short ones)
+    main_id = max(mains, key=lambda k: int(k))                    # the last one = the timed step of the bench command
     m = per[main_id]
     rd = m["dram__bytes_read.sum"][0] * scale[m["dram__bytes_read.sum"][1]]
     wr = m["dram__bytes_write.sum"][0] * scale[m["dram__bytes_write.sum"][1]]
