@@ -133,11 +133,15 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
     def __init__(self, device):
+        """device: an ordinal or a comma-separated list of ordinals; None = do not sample (ranks other than 0: one
+        nvidia-smi process watches every GPU of the job, eight of them polling the driver would perturb it)"""
         self.device = device
         self.rows = []
         self.proc = None
 
     def __enter__(self):
+        if self.device is None:
+            return self
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device),
@@ -399,7 +403,7 @@ def main():
     alg_bytes = 0.0
     a_null = A_NULL[w["graph"][0]]
     hist = np.zeros(64, dtype=np.int64)
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(",".join(str(i) for i in range(world)) if rank == 0 else None) as clocks:
         wall0 = time.perf_counter()
         for s in range(args.steps):
             tc0 = time.perf_counter()

