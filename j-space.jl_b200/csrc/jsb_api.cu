@@ -29,11 +29,16 @@ namespace {
 
 thread_local std::string g_err;
 
-// One pinned host staging buffer is kept between calls: pinning gigabytes costs seconds, the
-// event logs of an ensemble are that large, and callers typically run ensembles back to back.
+// Pinned host blocks are kept between calls: pinning gigabytes costs seconds, the event logs of an ensemble are
+// that large, and callers typically run ensembles back to back.  One block per concurrent jsb_run shard (a call
+// with devices[] runs one shard per device, each with its own outputs), at most kPinKeep of them.
+// No more blocks exist (cached + handed out) than were ever in use at the same time, and never more than kPinKeep
+// are cached: a caller that runs one ensemble at a time keeps one block.
+constexpr int kPinKeep = 8;
 std::mutex g_pin_mu;
-void* g_pin_ptr = nullptr;
-size_t g_pin_bytes = 0;
+struct PinBlock { void* p; size_t bytes; };
+std::vector<PinBlock> g_pin;
+int g_pin_out = 0, g_pin_out_max = 1;
 
 // JSB_TIMING=1: phase timings of jsb_run on stderr
 struct PhaseTimer {
@@ -48,14 +53,19 @@ struct PhaseTimer {
   }
 };
 
+// the smallest cached block of at least `bytes`, else a fresh one
 void* pinned_take(size_t bytes, size_t* got) {
   {
     std::lock_guard<std::mutex> lk(g_pin_mu);
-    if (g_pin_ptr && g_pin_bytes >= bytes) {
-      void* p = g_pin_ptr;
-      *got = g_pin_bytes;
-      g_pin_ptr = nullptr;
-      g_pin_bytes = 0;
+    int best = -1;
+    for (int i = 0; i < (int)g_pin.size(); ++i)
+      if (g_pin[i].bytes >= bytes && (best < 0 || g_pin[i].bytes < g_pin[best].bytes)) best = i;
+    ++g_pin_out;
+    g_pin_out_max = std::max(g_pin_out_max, g_pin_out);
+    if (best >= 0) {
+      void* p = g_pin[best].p;
+      *got = g_pin[best].bytes;
+      g_pin.erase(g_pin.begin() + best);
       return p;
     }
   }
@@ -67,31 +77,57 @@ void* pinned_take(size_t bytes, size_t* got) {
   if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
     cudaGetLastError();
     want = bytes;
-    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      std::lock_guard<std::mutex> lk(g_pin_mu);
+      --g_pin_out;
+      return nullptr;
+    }
   }
   *got = want;
   return p;
 }
 
-// the cached block, whatever its size (streamed outputs write into it while the kernel is still running)
+// the largest cached block, whatever its size (streamed outputs write into it while the kernel is still running)
 void* pinned_take_cached(size_t* got) {
   std::lock_guard<std::mutex> lk(g_pin_mu);
-  void* p = g_pin_ptr;
-  *got = g_pin_bytes;
-  g_pin_ptr = nullptr;
-  g_pin_bytes = 0;
+  int best = -1;
+  for (int i = 0; i < (int)g_pin.size(); ++i)
+    if (best < 0 || g_pin[i].bytes > g_pin[best].bytes) best = i;
+  if (best < 0) { *got = 0; return nullptr; }
+  ++g_pin_out;
+  g_pin_out_max = std::max(g_pin_out_max, g_pin_out);
+  void* p = g_pin[best].p;
+  *got = g_pin[best].bytes;
+  g_pin.erase(g_pin.begin() + best);
   return p;
 }
 
 void pinned_give(void* p, size_t bytes) {
   if (!p) return;
-  void* drop = nullptr;
+  std::vector<void*> drop;
   {
     std::lock_guard<std::mutex> lk(g_pin_mu);
-    if (bytes > g_pin_bytes) { drop = g_pin_ptr; g_pin_ptr = p; g_pin_bytes = bytes; }
-    else drop = p;
+    if (g_pin_out > 0) --g_pin_out;
+    g_pin.push_back({p, bytes});
+    while ((int)g_pin.size() > kPinKeep || (int)g_pin.size() + g_pin_out > g_pin_out_max) {  // drop the smallest
+      int worst = 0;
+      for (int i = 1; i < (int)g_pin.size(); ++i)
+        if (g_pin[i].bytes < g_pin[worst].bytes) worst = i;
+      drop.push_back(g_pin[worst].p);
+      g_pin.erase(g_pin.begin() + worst);
+    }
   }
-  if (drop) cudaFreeHost(drop);
+  for (void* d : drop) cudaFreeHost(d);
+}
+
+void pinned_drop_all() {
+  std::vector<PinBlock> all;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    all.swap(g_pin);
+  }
+  for (auto& b : all) cudaFreeHost(b.p);
 }
 
 int fail(int code, const char* fmt, ...) {
@@ -718,12 +754,7 @@ void jsb_trim(void) {
     for (auto& b : g_devs[d].buf) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
   }
   cudaSetDevice(cur);
-  void* drop = nullptr;
-  {
-    std::lock_guard<std::mutex> lk(g_pin_mu);
-    drop = g_pin_ptr; g_pin_ptr = nullptr; g_pin_bytes = 0;
-  }
-  if (drop) cudaFreeHost(drop);
+  pinned_drop_all();
 }
 
 }  // extern "C"
