@@ -157,7 +157,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def window(self, t0, t1):
+        """Only the samples that arrived inside the timed region [t0, t1] count (the sampler is started before the
+        warm-up so that the start-up of nvidia-smi, which holds driver locks, does not land in the timed region)."""
+        self.t0, self.t1 = t0, t1
 
     def __exit__(self, *a):
         if self.proc:
@@ -171,7 +176,10 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        for ts, r in self.rows:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.3):
+                continue
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -389,6 +397,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(",".join(str(i) for i in range(world)) if rank == 0 else None)
+    clocks.__enter__()
     for i in range(args.warmup):
         step(BASE_SEED + 1000 + i).close()
 
@@ -403,7 +413,7 @@ def main():
     alg_bytes = 0.0
     a_null = A_NULL[w["graph"][0]]
     hist = np.zeros(64, dtype=np.int64)
-    with ClockSampler(",".join(str(i) for i in range(world)) if rank == 0 else None) as clocks:
+    try:
         wall0 = time.perf_counter()
         for s in range(args.steps):
             tc0 = time.perf_counter()
@@ -423,6 +433,9 @@ def main():
             r.close()
         barrier()
         wall = time.perf_counter() - wall0
+        clocks.window(wall0, wall0 + wall)
+    finally:
+        clocks.__exit__(None, None, None)
     t = torch.tensor([kernel_ms, wall, call_s * 1e3], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(iters), float(eff), alg_bytes, float(launches), float(d2h)], dtype=torch.float64,
                        device="cuda")

@@ -610,10 +610,18 @@ done:
 
 // Per-device state: one lock that serialises jsb_run on a device (launch configuration of the kernels and the
 // cached buffers below are per device), and the large device buffers kept between calls.
-enum { BUF_WS, BUF_LOG, BUF_CHUNK_OWNER, BUF_CHUNK_SEQ, BUF_GATHER, BUF_OUT_CLONE, BUF_OUT_CELL, BUF_OUT_LISTS, BUF_CLONES, BUF_SUSP, BUF_N };
+// (the small per-call tables are cached too: every cudaMalloc / cudaFree / cudaHostAlloc takes the driver lock, and a
+// monitoring tool polling the same GPU — nvidia-smi in bench.py — can hold that lock for tens of milliseconds)
+enum { BUF_WS, BUF_LOG, BUF_CHUNK_OWNER, BUF_CHUNK_SEQ, BUF_GATHER, BUF_OUT_CLONE, BUF_OUT_CELL, BUF_OUT_LISTS, BUF_CLONES, BUF_SUSP,
+       BUF_POINTS, BUF_DPOOL, BUF_IPOOL, BUF_SUM, BUF_COUNTERS, BUF_CLONE_OFF, BUF_CHUNK_NEXT, BUF_SNAPS, BUF_FIN, BUF_FIN_CTR,
+       BUF_CHUNK_PREV, BUF_PRIO, BUF_ORDER, BUF_N };
 struct DeviceState {
   std::mutex mu;
   struct Buf { void* p = nullptr; size_t bytes = 0; } buf[BUF_N];
+  void* h_scratch = nullptr;   // small pinned block (finish list of the streamed outputs)
+  size_t h_scratch_bytes = 0;
+  cudaStream_t stream = nullptr, stream2 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 DeviceState g_devs[64];
 
@@ -747,11 +755,17 @@ void jsb_trim(void) {
   const int ndev = jsb_device_count();
   for (int d = 0; d < ndev && d < 64; ++d) {
     std::lock_guard<std::mutex> lk(g_devs[d].mu);
-    bool any = false;
+    bool any = g_devs[d].stream || g_devs[d].h_scratch;
     for (auto& b : g_devs[d].buf) any = any || b.p;
     if (!any) continue;
     cudaSetDevice(d);
     for (auto& b : g_devs[d].buf) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+    DeviceState& t = g_devs[d];
+    if (t.h_scratch) { cudaFreeHost(t.h_scratch); t.h_scratch = nullptr; t.h_scratch_bytes = 0; }
+    if (t.stream) { cudaStreamDestroy(t.stream); t.stream = nullptr; }
+    if (t.stream2) { cudaStreamDestroy(t.stream2); t.stream2 = nullptr; }
+    if (t.ev0) { cudaEventDestroy(t.ev0); t.ev0 = nullptr; }
+    if (t.ev1) { cudaEventDestroy(t.ev1); t.ev1 = nullptr; }
   }
   cudaSetDevice(cur);
   pinned_drop_all();
@@ -822,7 +836,8 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
     CUDA_TRY(cudaSetDevice(device));
     rc = upload_graph(g, device, &gd);
     if (rc != JSB_OK) goto done;
-    CUDA_TRY(cudaStreamCreate(&stream));
+    if (!ds.stream) CUDA_TRY(cudaStreamCreate(&ds.stream));
+    stream = ds.stream;
     {  // the kernels need 8 KB of stack per thread; never lower what the host application has set
       size_t cur_stack = 0;
       CUDA_TRY(cudaDeviceGetLimit(&cur_stack, cudaLimitStackSize));
@@ -860,9 +875,9 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
       }
     }
     res->max_snap = max_snap;
-    CUDA_TRY(cudaMalloc(&d_points, sizeof(DevPoint) * hp.size()));
-    CUDA_TRY(cudaMalloc(&d_dpool, sizeof(double) * dpool.size()));
-    CUDA_TRY(cudaMalloc(&d_ipool, sizeof(int32_t) * ipool.size()));
+    DEV_BUF(d_points, DevPoint*, BUF_POINTS, sizeof(DevPoint) * hp.size());
+    DEV_BUF(d_dpool, double*, BUF_DPOOL, sizeof(double) * dpool.size());
+    DEV_BUF(d_ipool, int32_t*, BUF_IPOOL, sizeof(int32_t) * ipool.size());
     CUDA_TRY(cudaMemcpyAsync(d_points, hp.data(), sizeof(DevPoint) * hp.size(), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(d_dpool, dpool.data(), sizeof(double) * dpool.size(), cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(d_ipool, ipool.data(), sizeof(int32_t) * ipool.size(), cudaMemcpyHostToDevice, stream));
@@ -942,12 +957,12 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
     DEV_BUF(d_ws, uint8_t*, BUF_WS, L.total * slots);
 
     // ---- outputs --------------------------------------------------------------------------
-    CUDA_TRY(cudaMalloc(&d_sum, sizeof(jsb_summary) * n_local));
-    CUDA_TRY(cudaMalloc(&d_counters, sizeof(unsigned long long) * 3));
+    DEV_BUF(d_sum, jsb_summary*, BUF_SUM, sizeof(jsb_summary) * n_local);
+    DEV_BUF(d_counters, unsigned long long*, BUF_COUNTERS, sizeof(unsigned long long) * 3);
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, sizeof(unsigned long long) * 3, stream));
     unsigned long long clone_cap = std::min<unsigned long long>((unsigned long long)n_local * kMaxClones, 8ull << 20);
     DEV_BUF(d_clones, jsb_clone*, BUF_CLONES, sizeof(jsb_clone) * clone_cap);
-    CUDA_TRY(cudaMalloc(&d_clone_off, sizeof(long long) * n_local));
+    DEV_BUF(d_clone_off, long long*, BUF_CLONE_OFF, sizeof(long long) * n_local);
     uint32_t n_chunks = 0;
     const bool ret_series = (opts->flags & JSB_OUT_SERIES) != 0 && !fast_mode;
     const bool ret_events = (opts->flags & JSB_OUT_EVENTS) != 0;
@@ -959,13 +974,13 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
       want = std::min<uint64_t>(want, free_b / 3);
       n_chunks = (uint32_t)std::max<uint64_t>(1, want / (sizeof(jsb_event) * kLogChunk));
       DEV_BUF(d_log, jsb_event*, BUF_LOG, sizeof(jsb_event) * kLogChunk * (size_t)n_chunks);
-      CUDA_TRY(cudaMalloc(&d_chunk_next, sizeof(uint32_t)));
+      DEV_BUF(d_chunk_next, uint32_t*, BUF_CHUNK_NEXT, sizeof(uint32_t));
       CUDA_TRY(cudaMemsetAsync(d_chunk_next, 0, sizeof(uint32_t), stream));
       DEV_BUF(d_chunk_owner, int32_t*, BUF_CHUNK_OWNER, sizeof(int32_t) * n_chunks);
       DEV_BUF(d_chunk_seq, uint32_t*, BUF_CHUNK_SEQ, sizeof(uint32_t) * n_chunks);
     }
     if (max_snap > 0) {
-      CUDA_TRY(cudaMalloc(&d_snaps, sizeof(jsb_snapshot) * (size_t)max_snap * n_local));
+      DEV_BUF(d_snaps, jsb_snapshot*, BUF_SNAPS, sizeof(jsb_snapshot) * (size_t)max_snap * n_local);
       CUDA_TRY(cudaMemsetAsync(d_snaps, 0xFF, sizeof(jsb_snapshot) * (size_t)max_snap * n_local, stream));
     }
     if (opts->flags & JSB_OUT_LATTICE) {
@@ -1012,9 +1027,9 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
         d_gather = (jsb_event*)ds.buf[BUF_GATHER].p;
         a.gather_out = d_gather;
         a.gather_cap = std::min<uint64_t>((res->pinned_bytes - fixed) / sizeof(jsb_event), ds.buf[BUF_GATHER].bytes / sizeof(jsb_event));
-        CUDA_TRY(cudaMalloc(&d_fin, sizeof(uint4) * (size_t)n_local));
-        CUDA_TRY(cudaMalloc(&d_fin_ctr, sizeof(unsigned long long)));
-        CUDA_TRY(cudaMalloc(&d_chunk_prev, sizeof(uint32_t) * n_chunks));
+        DEV_BUF(d_fin, uint4*, BUF_FIN, sizeof(uint4) * (size_t)n_local);
+        DEV_BUF(d_fin_ctr, unsigned long long*, BUF_FIN_CTR, sizeof(unsigned long long));
+        DEV_BUF(d_chunk_prev, uint32_t*, BUF_CHUNK_PREV, sizeof(uint32_t) * n_chunks);
         CUDA_TRY(cudaMemsetAsync(d_fin, 0xFF, sizeof(uint4) * (size_t)n_local, stream));
         CUDA_TRY(cudaMemsetAsync(d_fin_ctr, 0, sizeof(unsigned long long), stream));
         a.fin_list = d_fin; a.fin_ctr = d_fin_ctr; a.chunk_prev = d_chunk_prev;
@@ -1035,8 +1050,8 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
     uint32_t* d_susp_state = nullptr;
     const uint64_t susp_stride = (L.total + susp_extra_bytes(site_bytes) + 255) & ~uint64_t(255);
     if (use_pilot) {
-      CUDA_TRY(cudaMalloc(&d_prio, sizeof(float) * n_local));
-      CUDA_TRY(cudaMalloc(&d_order, sizeof(uint32_t) * n_local));
+      DEV_BUF(d_prio, float*, BUF_PRIO, sizeof(float) * n_local);
+      DEV_BUF(d_order, uint32_t*, BUF_ORDER, sizeof(uint32_t) * n_local);
       // Suspending pilot (jsb_kernels.cu, susp_save / susp_restore): when the parked states of every replicate fit
       // comfortably into device memory the pilot pass is the first stretch of the real run (all outputs on) and the
       // full pass resumes it, so the pilot costs nothing but two workspace copies per replicate.  Otherwise the
@@ -1056,8 +1071,9 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
       }
     }
     pt.mark("setup + allocations");
-    CUDA_TRY(cudaEventCreate(&ev0));
-    CUDA_TRY(cudaEventCreate(&ev1));
+    if (!ds.ev0) CUDA_TRY(cudaEventCreate(&ds.ev0));
+    if (!ds.ev1) CUDA_TRY(cudaEventCreate(&ds.ev1));
+    ev0 = ds.ev0; ev1 = ds.ev1;
     CUDA_TRY(cudaEventRecord(ev0, stream));
     // Longest-first scheduling for ensembles of a few replicates per warp slot: a short pilot pass (8192
     // iterations per replicate; its work estimate has rank correlation ~0.97 with the final iteration
@@ -1113,8 +1129,17 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
     // the kernel ends only the last few logs are left to copy.  When the buffers of the earlier call turn out too
     // small for this one, everything is gathered and copied after the kernel as before.
     if (want_stream) {
-      CUDA_TRY(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
-      CUDA_TRY(cudaHostAlloc(&h_fin, sizeof(uint4) * (size_t)n_local + 64, cudaHostAllocDefault));
+      if (!ds.stream2) CUDA_TRY(cudaStreamCreateWithFlags(&ds.stream2, cudaStreamNonBlocking));
+      stream2 = ds.stream2;
+      {
+        const size_t hb = sizeof(uint4) * (size_t)n_local + 64;
+        if (ds.h_scratch_bytes < hb) {
+          if (ds.h_scratch) { cudaFreeHost(ds.h_scratch); ds.h_scratch = nullptr; ds.h_scratch_bytes = 0; }
+          CUDA_TRY(cudaHostAlloc(&ds.h_scratch, hb + hb / 4, cudaHostAllocDefault));
+          ds.h_scratch_bytes = hb + hb / 4;
+        }
+        h_fin = ds.h_scratch;
+      }
       uint4* h_list = (uint4*)h_fin;
       unsigned long long* h_ctr = (unsigned long long*)(h_list + n_local);
       uint64_t processed = 0;
@@ -1300,16 +1325,14 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
   }
 
 done:
-  // (d_ws, d_log, the chunk tables, d_gather, the lattice / list outputs and d_clones belong to the device cache)
-  cudaFree(d_points); cudaFree(d_dpool); cudaFree(d_ipool); cudaFree(d_sum);
-  cudaFree(d_counters); cudaFree(d_clone_off); cudaFree(d_chunk_next);
-  cudaFree(d_fin); cudaFree(d_fin_ctr); cudaFree(d_chunk_prev); cudaFree(d_ser_meta); cudaFree(d_series);
-  if (h_fin) cudaFreeHost(h_fin);
-  if (stream2) cudaStreamDestroy(stream2);
-  cudaFree(d_ev_off); cudaFree(d_snaps); cudaFree(d_order); cudaFree(d_prio); cudaFree(d_trace);
-  if (ev0) cudaEventDestroy(ev0);
-  if (ev1) cudaEventDestroy(ev1);
-  if (stream) cudaStreamDestroy(stream);
+  // (every buffer, stream and event a normal call uses belongs to the device cache; what is freed here are the
+  // tables of the rarer paths: gather after the kernel, series, trace)
+  if (stream) cudaStreamSynchronize(stream);   // nothing of this call is in flight when the lock is released
+  if (stream2) cudaStreamSynchronize(stream2);
+  if (d_ser_meta) cudaFree(d_ser_meta);
+  if (d_series) cudaFree(d_series);
+  if (d_ev_off) cudaFree(d_ev_off);
+  if (d_trace) cudaFree(d_trace);
   cudaSetDevice(prev_dev);
   pt.mark("free");
   if (rc != JSB_OK) { delete res; return rc; }
