@@ -936,6 +936,12 @@ void orc_mt_raw(uint64_t mt_seed, uint64_t* out, int64_t n) {
   jmt::MersenneTwister m(mt_seed, v);
   for (int64_t k = 0; k + 1 < n; k += 2) m.ds.next(out + k);
 }
+// the first n values rand(MersenneTwister(seed), UInt64) returns (integer cache of julia_mt.hpp)
+void orc_mt_u64(uint64_t mt_seed, int64_t n, uint64_t* out) {
+  jmt::Variant v;
+  jmt::MersenneTwister m(mt_seed, v);
+  for (int64_t k = 0; k < n; ++k) out[k] = m.rand_u64();
+}
 // pinning aid: out[k] = the value randn() returns when its first raw double is dSFMT output k of
 // MersenneTwister(seed) and the ziggurat accepts at once (NaN otherwise: 1.2 % of the calls)
 void orc_mt_randn_scan(uint64_t mt_seed, int64_t n, double* out) {
