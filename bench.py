@@ -147,7 +147,7 @@ class ClockSampler:
                 ["nvidia-smi", "-i", str(self.device),
                  "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"],
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "500"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
