@@ -446,6 +446,7 @@ struct jsb_result {
   jsb_event* events = nullptr;  // replicate-major
   std::vector<uint64_t> ev_off;  // n_local + 1: first row of every replicate (streamed outputs: in finish order)
   std::vector<uint64_t> ev_cnt;  // n_local: rows of every replicate
+  std::vector<uint32_t> lat_slot; // streamed outputs: lattice / lists of replicate i sit in slot lat_slot[i] (its finish rank); empty: slot i
   uint16_t* lat_clone = nullptr;
   uint32_t* lat_cell = nullptr;
   uint32_t* lists = nullptr;
@@ -1165,6 +1166,16 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
             const uint64_t e0 = ((uint64_t)h_list[processed].w << 32) | h_list[processed].z;
             const uint64_t e1 = (((uint64_t)h_list[k - 1].w << 32) | h_list[k - 1].z) + h_list[k - 1].y;
             if (e1 > e0) CUDA_TRY(cudaMemcpyAsync(h_events + e0, d_gather + e0, sizeof(jsb_event) * (e1 - e0), cudaMemcpyDeviceToHost, stream2));
+            {  // lattices and lists of these ranks: slots [processed, k) are contiguous
+              uint8_t* hb = (uint8_t*)res->pinned;
+              const size_t nvz = (size_t)g->nv, r0 = (size_t)processed, nr = (size_t)(k - processed);
+              if (opts->flags & JSB_OUT_LATTICE) {
+                CUDA_TRY(cudaMemcpyAsync(hb + sizeof(uint16_t) * nvz * r0, d_out_clone + nvz * r0, sizeof(uint16_t) * nvz * nr, cudaMemcpyDeviceToHost, stream2));
+                CUDA_TRY(cudaMemcpyAsync(hb + b_lc0 + sizeof(uint32_t) * nvz * r0, d_out_cell + nvz * r0, sizeof(uint32_t) * nvz * nr, cudaMemcpyDeviceToHost, stream2));
+              }
+              if (opts->flags & JSB_OUT_LISTS)
+                CUDA_TRY(cudaMemcpyAsync(hb + b_lc0 + b_li0 + sizeof(uint32_t) * 2 * nvz * r0, d_out_lists + 2 * nvz * r0, sizeof(uint32_t) * 2 * nvz * nr, cudaMemcpyDeviceToHost, stream2));
+            }
             processed = k;
           }
         }
@@ -1182,6 +1193,15 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
       }
     }
     CUDA_TRY(cudaStreamSynchronize(stream));
+    if (want_stream) {
+      // the kernel wrote lattices and lists by finish rank: the slot of every replicate, streamed or not
+      if (!streamed) {
+        fin_host.resize((size_t)n_local);
+        CUDA_TRY(cudaMemcpy(fin_host.data(), d_fin, sizeof(uint4) * (size_t)n_local, cudaMemcpyDeviceToHost));
+      }
+      res->lat_slot.assign((size_t)n_local, 0);
+      for (int64_t k = 0; k < n_local; ++k) res->lat_slot[fin_host[(size_t)k].x & 0x7FFFFFFFu] = (uint32_t)k;
+    }
     {
       float ms = 0.f;
       CUDA_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -1302,11 +1322,11 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
         if (ser_total) CUDA_TRY(cudaMemcpyAsync(res->series.data(), d_series, sizeof(jsb_series_row) * ser_total, cudaMemcpyDeviceToHost, stream));
         if (max_snap > 0) CUDA_TRY(cudaMemcpyAsync(res->ser_snap.data(), d_snap_rows, sizeof(long long) * nl * (size_t)max_snap, cudaMemcpyDeviceToHost, stream));
       }
-      if (opts->flags & JSB_OUT_LATTICE) {
+      if ((opts->flags & JSB_OUT_LATTICE) && !streamed) {
         CUDA_TRY(cudaMemcpyAsync(res->lat_clone, d_out_clone, sizeof(uint16_t) * (size_t)g->nv * n_local, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(res->lat_cell, d_out_cell, sizeof(uint32_t) * (size_t)g->nv * n_local, cudaMemcpyDeviceToHost, stream));
       }
-      if (opts->flags & JSB_OUT_LISTS)
+      if ((opts->flags & JSB_OUT_LISTS) && !streamed)
         CUDA_TRY(cudaMemcpyAsync(res->lists, d_out_lists, sizeof(uint32_t) * 2 * (size_t)g->nv * n_local, cudaMemcpyDeviceToHost, stream));
       CUDA_TRY(cudaStreamSynchronize(stream));
     }
@@ -1393,8 +1413,9 @@ int jsb_result_lattice(const jsb_result* r, int64_t i, const uint16_t** clone, c
   CHECK_INDEX(r, i);
   if (!(r->flags & JSB_OUT_LATTICE)) return fail(JSB_EINVAL, "run did not request JSB_OUT_LATTICE");
   r = part_of(r, i);
-  if (clone) *clone = r->lat_clone + (size_t)i * r->nv;
-  if (cell_id) *cell_id = r->lat_cell + (size_t)i * r->nv;
+  const size_t slot = r->lat_slot.empty() ? (size_t)i : (size_t)r->lat_slot[(size_t)i];
+  if (clone) *clone = r->lat_clone + slot * r->nv;
+  if (cell_id) *cell_id = r->lat_cell + slot * r->nv;
   return JSB_OK;
 }
 
@@ -1405,7 +1426,7 @@ int jsb_result_list(jsb_result* r, int64_t i, int32_t list, const uint32_t** p, 
   r = part_of(r, i);
   const jsb_summary& s = r->summaries[i];
   if (list < 0 || list > (int32_t)s.n_clones) return fail(JSB_EINVAL, "list %d is outside 0..n_clones", list);
-  const uint32_t* base = r->lists + (size_t)i * 2 * r->nv;
+  const uint32_t* base = r->lists + (r->lat_slot.empty() ? (size_t)i : (size_t)r->lat_slot[(size_t)i]) * 2 * r->nv;
   if (list == 0) { *p = base; *n = s.n_alive; return JSB_OK; }
   const jsb_clone* c;
   int32_t nc;

@@ -1691,6 +1691,15 @@ __device__ __noinline__ void write_outputs(Ctx<T>& X, Rep& r) {
     s.status = r.status;
     A.summaries[X.local_idx] = s;
   }
+  // streamed outputs: finish rank and first log row, one atomic; lattice and lists go to slot `rank` so that the
+  // host can copy completed runs of ranks as contiguous blocks
+  unsigned long long fin_stored = 0, fin_old = 0;
+  if (A.fin_list) {
+    if (A.flags & JSB_OUT_EVENTS) fin_stored = r.log_on ? r.nlog : r.nstored;
+    if (lane == 0) fin_old = atomicAdd(A.fin_ctr, (1ull << 40) + fin_stored);
+    fin_old = __shfl_sync(FULL, fin_old, 0);
+  }
+  const size_t out_slot = A.fin_list ? (size_t)(fin_old >> 40) : (size_t)X.local_idx;
   long long off = -1;
   if (A.clone_pool) {
     unsigned long long o = 0;
@@ -1710,8 +1719,8 @@ __device__ __noinline__ void write_outputs(Ctx<T>& X, Rep& r) {
     if (lane == 0) A.clone_off[X.local_idx] = off;
   }
   if (A.out_clone) {
-    uint16_t* oc = A.out_clone + (size_t)X.local_idx * nv;
-    uint32_t* oi = A.out_cell + (size_t)X.local_idx * nv;
+    uint16_t* oc = A.out_clone + out_slot * nv;
+    uint32_t* oi = A.out_cell + out_slot * nv;
     for (uint32_t v = lane; v < nv; v += 32) {
       uint16_t cl = X.clone[v];
       oc[v] = cl;
@@ -1719,7 +1728,7 @@ __device__ __noinline__ void write_outputs(Ctx<T>& X, Rep& r) {
     }
   }
   if (A.out_lists) {
-    uint32_t* la = A.out_lists + (size_t)X.local_idx * 2 * nv;
+    uint32_t* la = A.out_lists + out_slot * 2 * nv;
     uint32_t* ll = la + nv;
     for (uint32_t i = lane; i < r.n; i += 32) la[i] = a_get(X, i) + 1;
     uint32_t wpos = 0;
@@ -1731,10 +1740,7 @@ __device__ __noinline__ void write_outputs(Ctx<T>& X, Rep& r) {
   }
   __syncwarp();
   if (A.fin_list) {
-    unsigned long long stored = 0, old = 0;
-    if (A.flags & JSB_OUT_EVENTS) stored = r.log_on ? r.nlog : r.nstored;
-    if (lane == 0) old = atomicAdd(A.fin_ctr, (1ull << 40) + stored);
-    old = __shfl_sync(FULL, old, 0);
+    const unsigned long long stored = fin_stored, old = fin_old;
     const unsigned long long first = old & ((1ull << 40) - 1ull);
     const uint32_t rank = (uint32_t)(old >> 40);
     bool packed = stored == 0;
