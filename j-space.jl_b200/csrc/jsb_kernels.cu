@@ -960,6 +960,12 @@ __device__ __forceinline__ void refold(Ctx<T>& X, Rep& r) {
   // the shared-memory carve-out this kernel uses), so sixteen loads per lane are put in flight at once and the lines are asked to stay in L1.
   const uint32_t sB = X.sB, sLen = X.sLen;
   SUB_T0();
+  if (S - from <= 32u) {
+    // few clones to re-weigh (every event of a sweep with a tiny driver rate, the early phase of every replicate):
+    // one load per lane instead of the sixteen-deep pipeline below
+    const uint32_t i = from + (uint32_t)lane;
+    if (i < S) sts_f64(sB + i * 8u, ldg_keep_f64(alpha + i) * (double)lds_tab<T>(sLen, i));  // :693
+  } else
   for (uint32_t base = from; base < S; base += 512u) {
     double a[16];
 #pragma unroll
