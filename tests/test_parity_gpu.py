@@ -350,3 +350,30 @@ def test_device_side_series_equals_oracle_series_and_log_replay(jsb, oracle, rul
     assert exact >= 20
     only_series.close()
     both.close()
+
+
+def test_output_flag_combinations_agree(jsb, monkeypatch):
+    # every combination of output flags goes through a different mix of paths (pilot parked/resumed, streamed or
+    # gathered outputs, series reduction, slots by finish rank or by index): the outputs they share must be identical,
+    # on a first round of calls and on a second one that finds the cached host / device buffers
+    from jspace_b200 import _lib as L
+    monkeypatch.setenv("JSB_DEBUG_GRID", "4")
+    monkeypatch.setenv("JSB_PILOT_ITERS", "500")
+    g = jsb.Graph.lattice(50, 50, 2)
+    p = jsb.Point(Tf=80.0, rate_birth=0.3, rate_death=0.02, rate_migration=0.01, mu_driver=0.02, adv_mean=0.4, adv_std=0.1,
+                  rule="contact", t_bottleneck=[30.0], ratio_bottleneck=[0.5])
+    ref = None
+    for rnd in range(2):
+        for flags in (L.OUT_EVENTS | L.OUT_LATTICE | L.OUT_LISTS, L.OUT_LATTICE, L.OUT_LISTS, L.OUT_LATTICE | L.OUT_LISTS,
+                      L.OUT_SERIES | L.OUT_LATTICE, L.OUT_EVENTS, 0):
+            r = jsb.run_ensemble(g, p, 64, seed=9, flags=flags, warps_per_sm=2)
+            lat = [r.lattice(i)[0].tobytes() + r.lattice(i)[1].tobytes() for i in range(64)] if flags & L.OUT_LATTICE else None
+            lis = [r.list(i, 0).tobytes() + r.list(i, 1).tobytes() for i in range(64)] if flags & L.OUT_LISTS else None
+            evs = [r.events(i).tobytes() for i in range(64)] if flags & L.OUT_EVENTS else None
+            if ref is None:
+                ref = dict(sm=r.summaries.tobytes(), lat=lat, lis=lis, evs=evs)
+            assert r.summaries.tobytes() == ref["sm"], (rnd, flags)
+            assert lat is None or lat == ref["lat"], (rnd, flags)
+            assert lis is None or lis == ref["lis"], (rnd, flags)
+            assert evs is None or evs == ref["evs"], (rnd, flags)
+            r.close()
