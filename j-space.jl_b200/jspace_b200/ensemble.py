@@ -153,6 +153,41 @@ class Point:
         return p
 
 
+def series_from_rows(rows, rows_before_snapshot=(), n0: int = 1):
+    """jsb_series_row records -> (list_len_node_occ, CA_Alive_TOT).  One push per run of rows that ends with a row
+    without SERIES_MORE; `gain` beyond the number of clones seen so far is a new clone of one cell; a snapshot
+    inserts a copy of the current counts before the push at its row position (src/J_Space.jl:712)."""
+    n_occ = [int(n0)]
+    counts = [int(n0)] if n0 else []
+    ca_tot = []
+    snap_at = sorted(int(x) for x in rows_before_snapshot)
+    si = 0
+    k = 0
+    while k < len(rows):
+        while si < len(snap_at) and snap_at[si] <= k:
+            ca_tot.append(list(counts))
+            si += 1
+        while True:
+            r = rows[k]
+            if r["loss"]:
+                counts[int(r["loss"]) - 1] -= 1
+            if r["gain"]:
+                g = int(r["gain"])
+                if g > len(counts):
+                    counts.append(1)
+                else:
+                    counts[g - 1] += 1
+            k += 1
+            if not (int(r["n_alive"]) & L.SERIES_MORE):
+                break
+        n_occ.append(int(r["n_alive"]) & 0x7FFFFFFF)
+        ca_tot.append(list(counts))
+    while si < len(snap_at):
+        ca_tot.append(list(counts))
+        si += 1
+    return n_occ, ca_tot
+
+
 class EnsembleResult:
     """Owns a jsb_result."""
 
@@ -209,35 +244,7 @@ class EnsembleResult:
         """(list_len_node_occ, CA_Alive_TOT) of replicate i as the reference builds them (src/J_Space.jl:656-658,
         712, 740-741, 757-758, 807-808, 835-836), from the device-side series; n0 = number of starting cells."""
         rows, snaps = self.series_rows(i)
-        n_occ = [int(n0)]
-        counts = [int(n0)] if n0 else []
-        ca_tot = []
-        snap_at = sorted(int(x) for x in snaps)
-        si = 0
-        k = 0
-        while k < len(rows):
-            while si < len(snap_at) and snap_at[si] <= k:
-                ca_tot.append(list(counts))
-                si += 1
-            while True:  # one push: the rows up to the first one without SERIES_MORE
-                r = rows[k]
-                if r["loss"]:
-                    counts[int(r["loss"]) - 1] -= 1
-                if r["gain"]:
-                    g = int(r["gain"])
-                    if g > len(counts):
-                        counts.append(1)
-                    else:
-                        counts[g - 1] += 1
-                k += 1
-                if not (int(r["n_alive"]) & L.SERIES_MORE):
-                    break
-            n_occ.append(int(r["n_alive"]) & 0x7FFFFFFF)
-            ca_tot.append(list(counts))
-        while si < len(snap_at):
-            ca_tot.append(list(counts))
-            si += 1
-        return n_occ, ca_tot
+        return series_from_rows(rows, snaps, n0)
 
     def histogram(self, point: int, kind: int) -> np.ndarray:
         out = np.zeros(64, dtype=np.uint64)

@@ -66,3 +66,23 @@ def test_shard_ranges_partition_the_ensemble(jsb):
             assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in r]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_series_rows_to_reference_series():
+    # jsb_series_row -> list_len_node_occ / CA_Alive_TOT (host side of JSB_OUT_SERIES); the device side is compared with
+    # the oracle in tests/test_parity_gpu.py
+    import numpy as np
+    from jspace_b200 import _lib as L
+    from jspace_b200.ensemble import series_from_rows
+    M = L.SERIES_MORE
+    rows = np.array([(2, 1, 0),          # birth in clone 1
+                     (3, 2, 0),          # Mutation: clone 2 appears with one cell
+                     (3, 0, 0),          # migration
+                     (2, 0, 1),          # death in clone 1
+                     (2, 2, 1),          # voter birth of clone 2 displacing a cell of clone 1
+                     (1 | M, 0, 2), (0, 0, 2)],  # excision removing two cells of clone 2: one push
+                    dtype=L.SERIES_DTYPE)
+    n_occ, ca = series_from_rows(rows, rows_before_snapshot=[2, 7], n0=1)
+    assert n_occ == [1, 2, 3, 3, 2, 2, 0]
+    assert ca == [[2], [2, 1], [2, 1], [2, 1], [1, 1], [0, 2], [0, 0], [0, 0]]
+    assert series_from_rows(rows[:0], [0], n0=1) == ([1], [[1]])
