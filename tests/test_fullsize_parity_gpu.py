@@ -66,6 +66,18 @@ def test_pilot_order_and_counter_path_vs_oracle(jsb, oracle, monkeypatch):
     assert a[0].tobytes() == c[0].tobytes()
 
 
+def test_suspended_replicates_resume_in_tree_mode(jsb, oracle, monkeypatch):
+    # method 2 (driver tree, hvoter displacements, the every-iteration excision index of :1062-1064) parked and resumed
+    p = dict(method=2, Tf=60.0, rate_death=0.02, rate_migration=0.01, mu_driver=0.05, rule="hvoter", tree_edges=TREE_EDGES,
+             node_rate=TREE_RATES, root_node=0, root_rate=0.3, t_bottleneck=[20.0, 40.0], ratio_bottleneck=[0.5, 0.5],
+             t_snapshot=[15.0])
+    monkeypatch.setenv("JSB_DEBUG_GRID", "3")
+    monkeypatch.setenv("JSB_PILOT_ITERS", "256")
+    got = []
+    compare_runs(jsb, oracle, ("lattice", 3, 30, 30), p, seed=21, reps=36, warps_per_sm=2, summaries_out=got)
+    assert int((got[0]["n_iterations"] > 256).sum()) > 15
+
+
 def test_suspended_replicates_resume_with_snapshots_and_small_arena(jsb, oracle, monkeypatch):
     # resume with everything that lives across the interruption: snapshot index, excision index, event-log
     # chunks, a list arena that has been compacted, voter displacements
