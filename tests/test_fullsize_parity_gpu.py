@@ -109,6 +109,21 @@ def test_c4_100k_node_geometric_graph(jsb, oracle):
     assert len(rowptr) - 1 > 90000 and max(int(x["n_iterations"]) for x in s) > 10000
 
 
+def test_csr_u32_replicates_parked_and_resumed(jsb, oracle, monkeypatch):
+    # the large-state path (u32 site ids, CSR neighbour gathers, occupancy test in global memory) through the pilot:
+    # more replicates than warp slots, every one parked once and resumed, eight of them against the oracle
+    from graphs import random_geometric_csr, geometric_centre
+    rowptr, colidx, pts = random_geometric_csr(70000, seed=99, return_points=True)
+    assert len(rowptr) - 1 > 65535
+    monkeypatch.setenv("JSB_DEBUG_GRID", "4")
+    monkeypatch.setenv("JSB_PILOT_ITERS", "1000")
+    got = []
+    compare_runs(jsb, oracle, ("csr", rowptr, colidx), dict(C2, Tf=120.0, t_bottleneck=[60.0], ratio_bottleneck=[0.5]),
+                 seed=4, reps=24, warps_per_sm=2, candidates=[geometric_centre(pts)], only=[0, 1, 2, 5, 8, 13, 21, 23],
+                 summaries_out=got)
+    assert int((got[0]["n_iterations"] > 1000).sum()) > 12
+
+
 def test_c5_sweep_grid_corners(jsb, oracle):
     # b in {0.1..0.6} x d in {.005,.01,.02,.04} x adv_mean in {.1,.2,.4,.8}; the eight corners
     pts = [dict(Tf=200.0, rate_birth=b, rate_death=d, rate_migration=0.01, mu_driver=1e-5, adv_mean=a, adv_std=0.1,
