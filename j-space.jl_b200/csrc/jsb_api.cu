@@ -623,6 +623,9 @@ struct DeviceState {
   size_t h_scratch_bytes = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // answers of driver queries that do not change (asked once: a monitoring tool polling the GPU holds the lock they need)
+  bool have_prop = false, stack_ok = false;
+  cudaDeviceProp prop;
 };
 DeviceState g_devs[64];
 
@@ -839,10 +842,11 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
     if (rc != JSB_OK) goto done;
     if (!ds.stream) CUDA_TRY(cudaStreamCreate(&ds.stream));
     stream = ds.stream;
-    {  // the kernels need 8 KB of stack per thread; never lower what the host application has set
+    if (!ds.stack_ok) {  // the kernels need 8 KB of stack per thread; never lower what the host application has set
       size_t cur_stack = 0;
       CUDA_TRY(cudaDeviceGetLimit(&cur_stack, cudaLimitStackSize));
       if (cur_stack < 8192) CUDA_TRY(cudaDeviceSetLimit(cudaLimitStackSize, 8192));
+      ds.stack_ok = true;
     }
 
     // ---- sweep points ---------------------------------------------------------------------
@@ -884,8 +888,11 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
     CUDA_TRY(cudaMemcpyAsync(d_ipool, ipool.data(), sizeof(int32_t) * ipool.size(), cudaMemcpyHostToDevice, stream));
 
     // ---- launch geometry ------------------------------------------------------------------
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (!ds.have_prop) {
+      CUDA_TRY(cudaGetDeviceProperties(&ds.prop, device));
+      ds.have_prop = true;
+    }
+    const cudaDeviceProp& prop = ds.prop;
     RunArgs a;
     std::memset(&a, 0, sizeof a);
     a.g.nv = (uint32_t)g->nv;
@@ -969,10 +976,12 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
     const bool ret_events = (opts->flags & JSB_OUT_EVENTS) != 0;
     const bool log_needed = ret_events || ret_series;  // the series is a reduction of the log, done on the device
     if (log_needed) {
-      size_t free_b = 0, total_b = 0;
-      CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
       uint64_t want = opts->log_pool_bytes ? opts->log_pool_bytes : (1ull << 30);
-      want = std::min<uint64_t>(want, free_b / 3);
+      if (ds.buf[BUF_LOG].bytes < want) {  // a pool of that size is not cached yet: what the device can spare
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        want = std::min<uint64_t>(want, std::max<uint64_t>((uint64_t)(free_b + ds.buf[BUF_LOG].bytes) / 3, ds.buf[BUF_LOG].bytes));
+      }
       n_chunks = (uint32_t)std::max<uint64_t>(1, want / (sizeof(jsb_event) * kLogChunk));
       DEV_BUF(d_log, jsb_event*, BUF_LOG, sizeof(jsb_event) * kLogChunk * (size_t)n_chunks);
       DEV_BUF(d_chunk_next, uint32_t*, BUF_CHUNK_NEXT, sizeof(uint32_t));
@@ -1058,10 +1067,10 @@ int run_single(jsb_graph* g, const jsb_params* points, int64_t n_points, int64_t
       // full pass resumes it, so the pilot costs nothing but two workspace copies per replicate.  Otherwise the
       // pilot pass is thrown away as before.  JSB_NO_SUSPEND=1 forces the old behaviour.
       {
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
         const uint64_t need = susp_stride * (uint64_t)n_local + 4ull * n_local + 256;
         size_t have = ds.buf[BUF_SUSP].bytes;
+        size_t free_b = 0, total_b = 0;
+        if (need > have) cudaMemGetInfo(&free_b, &total_b);
         if (!std::getenv("JSB_NO_SUSPEND") && (need <= have || need <= (uint64_t)(free_b + have) / 2)) {
           uint8_t* blk = nullptr;
           DEV_BUF(blk, uint8_t*, BUF_SUSP, need);

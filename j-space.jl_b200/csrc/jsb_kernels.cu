@@ -2823,12 +2823,21 @@ __global__ void __launch_bounds__(MAXT, 1) ssa_kernel(const __grid_constant__ Ru
 
 // Chooses the shared-memory layout (tables + occupancy bitmask when it fits) and the number of
 // warps per block (one block per SM).
+// (device attributes and the function attributes last set are remembered per device: jsb_run serialises the calls
+// on a device, and every driver query skipped is one less wait on a lock that monitoring tools hold)
+struct PrepCache { int max_optin = 0, sm_max = 0, bytes = -1, pct = -1, fast_bytes = -1, fast_pct = -1; };
+static PrepCache g_prep[64];
+
 int ssa_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block) {
   const uint32_t words = (args.g.nv + 31) / 32;
   int dev = 0;
   cudaGetDevice(&dev);
-  int max_optin = 0;
-  if (cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
+  PrepCache& pc = g_prep[dev & 63];
+  if (pc.max_optin == 0) {
+    if (cudaDeviceGetAttribute(&pc.max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
+    cudaDeviceGetAttribute(&pc.sm_max, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+  }
+  const int max_optin = pc.max_optin;
   const size_t with_occ = ((smem_base_bytes(args.site_bytes) + 4ull * words + 15) & ~size_t(15)) + sizeof(HelpMail);
   const size_t without = ((smem_base_bytes(args.site_bytes) + 15) & ~size_t(15)) + sizeof(HelpMail);
   int cap = kMaxWarpsPerBlock;
@@ -2844,22 +2853,14 @@ int ssa_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block) {
   args.occ_words = use_occ ? words : 0;
   args.smem_per_warp = (uint32_t)(use_occ ? with_occ : without);
   const int bytes = (int)((size_t)args.smem_per_warp * w);
-  if (cudaFuncSetAttribute(ssa_kernel<uint16_t, kMaxWarpsPerBlock * 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(ssa_kernel<uint32_t, kMaxWarpsPerBlock * 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(ssa_kernel<uint16_t, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(ssa_kernel<uint32_t, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
-  {
-    // ask for no more shared-memory carve-out than the block needs: what is left of the 256 KB is the L1 that
-    // caches the member lists (hit rate ~57 %; every KB of carve-out taken from it was measurable)
-    int sm_max = 0;
-    cudaDeviceGetAttribute(&sm_max, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-    // rounded down: the driver never goes below what the block needs, and rounding up can skip a step
-    int pct = sm_max > 0 ? (int)(((long long)(bytes + 1024) * 100) / sm_max) : 100;
-    if (pct > 100) pct = 100;
-    cudaFuncSetAttribute(ssa_kernel<uint16_t, kMaxWarpsPerBlock * 32>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(ssa_kernel<uint32_t, kMaxWarpsPerBlock * 32>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(ssa_kernel<uint16_t, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    cudaFuncSetAttribute(ssa_kernel<uint32_t, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  (void)bytes;
+  if (pc.bytes != max_optin) {  // once per device: the largest opt-in size, every launch geometry fits under it
+    pc.bytes = -1;
+    if (cudaFuncSetAttribute(ssa_kernel<uint16_t, kMaxWarpsPerBlock * 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(ssa_kernel<uint32_t, kMaxWarpsPerBlock * 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(ssa_kernel<uint16_t, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(ssa_kernel<uint32_t, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin) != cudaSuccess) return -1;
+    pc.bytes = max_optin;
   }
   *warps_per_block = w;
   return 0;
@@ -2867,6 +2868,24 @@ int ssa_prepare(RunArgs& args, int max_warps_per_sm, int* warps_per_block) {
 
 int launch_ssa(const RunArgs& args, int grid_blocks, int warps_per_block, void* stream) {
   const size_t smem = (size_t)args.smem_per_warp * warps_per_block;
+  {
+    // ask for no more shared-memory carve-out than the block needs: what is left of the 256 KB is the L1 that
+    // caches the member lists (hit rate ~57 %; every KB of carve-out taken from it was measurable).  Set when the
+    // geometry changes, not per launch.
+    int dev = 0;
+    cudaGetDevice(&dev);
+    PrepCache& pc = g_prep[dev & 63];
+    // rounded down: the driver never goes below what the block needs, and rounding up can skip a step
+    int pct = pc.sm_max > 0 ? (int)(((long long)(smem + 1024) * 100) / pc.sm_max) : 100;
+    if (pct > 100) pct = 100;
+    if (pct != pc.pct) {
+      cudaFuncSetAttribute(ssa_kernel<uint16_t, kMaxWarpsPerBlock * 32>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(ssa_kernel<uint32_t, kMaxWarpsPerBlock * 32>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(ssa_kernel<uint16_t, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      cudaFuncSetAttribute(ssa_kernel<uint32_t, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      pc.pct = pct;
+    }
+  }
   const bool small_block = warps_per_block <= 8;
   if (args.site_bytes == 2) {
     if (small_block) ssa_kernel<uint16_t, 256><<<grid_blocks, warps_per_block * 32, smem, (cudaStream_t)stream>>>(args);
