@@ -936,6 +936,21 @@ void orc_mt_raw(uint64_t mt_seed, uint64_t* out, int64_t n) {
   jmt::MersenneTwister m(mt_seed, v);
   for (int64_t k = 0; k + 1 < n; k += 2) m.ds.next(out + k);
 }
+// slot layout of Set(1:n) under the Variant knobs: out[i] = key in slot i (0 = empty); returns the number of slots
+int64_t orc_intset_layout(int64_t n, const int32_t* variant, int64_t* out, int64_t cap) {
+  jmt::Variant v;
+  v.set_slots = variant[0]; v.sizehint_mode = variant[1]; v.hash_float = variant[2] != 0;
+  jmt::IntSet s = jmt::IntSet::range(n, v);
+  const int64_t sz = (int64_t)s.slots.size();
+  for (int64_t i = 0; i < sz && i < cap; ++i) out[i] = s.slots[i] == 1 ? s.keys[i] : 0;
+  return sz;
+}
+// n successive randexp() (kind 0) / randn() (kind 1) / rand() (kind 2) values of ONE MersenneTwister(seed)
+void orc_mt_seq(uint64_t mt_seed, int kind, int64_t n, double* out) {
+  jmt::Variant v;
+  jmt::MersenneTwister m(mt_seed, v);
+  for (int64_t k = 0; k < n; ++k) out[k] = kind == 0 ? m.randexp() : (kind == 1 ? m.randn() : m.rand_float());
+}
 // the first n values rand(MersenneTwister(seed), UInt64) returns (integer cache of julia_mt.hpp)
 void orc_mt_u64(uint64_t mt_seed, int64_t n, uint64_t* out) {
   jmt::Variant v;

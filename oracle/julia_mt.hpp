@@ -9,7 +9,8 @@
 //
 //   dSFMT-19937 (Saito & Matsumoto, dSFMT 2.2.x: do_recursion, init_by_array, period certification)
 //   Random.MersenneTwister: the 1002-double `vals` cache, the 501-UInt128 `ints` cache and its refill
-//       rand!(r, ::UnsafeView{UInt128}) (stdlib/Random/src/RNGs.jl), mt_pop! for UInt64 / UInt128
+//       mt_setfull!(r, ::Type{<:BitInteger}) of Julia 1.6+ (stdlib/Random/src/RNGs.jl; pinned by the manual's
+//       bitrand(MersenneTwister(1234), 10)), mt_pop! for UInt64 / UInt128
 //   rand(r) = pop - 1.0; rand(r, UInt52Raw()) = bits of the popped double
 //   rand(r, a:b) for one draw: SamplerRangeFast (RNGs.jl: `Sampler(::Type{MersenneTwister}, r, ::Val{1})`);
 //       inside rand(::Dict/::Set): SamplerRangeNDL on UInt64 draws (generation.jl, `Val(Inf)`)
@@ -293,36 +294,32 @@ struct MersenneTwister {
     raw_made += n2;
     for (int k = n2; k < n; ++k) A[k] = pop_bits();  // the tail comes from the scalar path
   }
-  // -- rand!(r, r.ints): 501 UInt128 out of 52-bit doubles, the missing 12 bits of every half taken from donors
+  // -- mt_setfull!(r, ::Type{<:BitInteger}) of Julia 1.6+ (stdlib/Random/src/RNGs.jl): dSFMT randomizes 52 of the 64
+  // bits of a word, so 627 UInt128 (1254 doubles, ONE fill_array! straight from the generator: the scalar cache is
+  // not touched) are condensed into 501 fully random ones — word 501+j donates 12 bits to each half of words
+  // 4j .. 4j+3 (shifts 48, 36, 24, 12), word 626 to word 500.  Pinned by the Julia manual's
+  // `bitrand(MersenneTwister(1234), 10)` (tests/test_reference_pin.py).
   void fill_ints() {
     if (var.test_float_start >= 0) {  // pinning aid: content irrelevant, scalar stream untouched
       for (int k = 0; k < 501; ++k) ints[k] = ((u128)0x9E3779B97F4A7C15ULL * (u128)(k + 1 + raw_made)) << 17;
       idxI = CACHE_I_BYTES;
       return;
     }
-    int n = 501, i = n;
-    uint64_t* F = reinterpret_cast<uint64_t*>(ints);
-    for (;;) {
-      fill_floats(F, 2 * i);  // the first pass fills everything, later passes only the donors just used up
-      if (n < 5) break;
-      i = 0;
-      while (n - i >= 5) {
-        const u128 u = ints[i++];          // A[i += 1]
-        ints[n - 1] ^= u << 48;            // A[n]
-        ints[n - 2] ^= u << 36;            // A[n -= 1]
-        ints[n - 3] ^= u << 24;
-        ints[n - 4] ^= u << 12;
-        n -= 4;
-      }
+    static thread_local uint64_t F[1254];
+    ds.fill(F, 1254);
+    raw_made += 1254;
+    u128 A[627];
+    for (int k = 0; k < 627; ++k) A[k] = (u128)F[2 * k] | ((u128)F[2 * k + 1] << 64);
+    int k = 501, n = 0;
+    while (n != 500) {
+      const u128 u = A[k++];
+      A[n++] ^= u << 48;
+      A[n++] ^= u << 36;
+      A[n++] ^= u << 24;
+      A[n++] ^= u << 12;
     }
-    if (n > 0) {
-      if (CACHE_F - idxF < 2) gen_rand();                 // reserve(r, 2) discards a single leftover double
-      const u128 hi = (u128)raw52(), lo = (u128)raw52();  // rand_ui2x52_raw: first pop is the high half
-      const u128 u = (hi << 64) | lo;
-      for (int k = 1; k <= n; ++k) ints[k - 1] ^= u << (12 * k);
-    }
-    if (var.refill_pad > 0) for (int k = 0; k < var.refill_pad; ++k) (void)pop_bits();
-    if (var.refill_pad < 0 && idxF + var.refill_pad >= 0) idxF += var.refill_pad;
+    A[500] ^= A[626] << 48;
+    for (int q = 0; q < 501; ++q) ints[q] = A[q];
     idxI = CACHE_I_BYTES;
   }
   uint64_t rand_u64() {

@@ -92,6 +92,35 @@ def test_mersenne_twister_known_answers(oracle):
     assert np.float32(e[0]) == np.float32(2.4835055)  # randexp(MersenneTwister(1234), Float32) = 2.4835055f0
 
 
+def test_mersenne_twister_sequences_of_the_julia_manual(oracle):
+    """Longer known answers from the Random docstrings of Julia 1.6-1.8 (recalled): `randexp!(MersenneTwister(1234),
+    zeros(5))`, the 3x3 `randexp` matrix that follows `randexp(rng, Float32)`, `randn(rng, ComplexF64)`, and
+    `bitrand(MersenneTwister(1234), 10)` — the last one pins the integer cache (mt_setfull! of Julia 1.6+: 627
+    UInt128 condensed into 501) and the order in which UInt64 values are popped from it."""
+    L = oracle.lib()
+    L.orc_mt_seq.argtypes = [C.c_uint64, C.c_int, C.c_int64, C.c_void_p]
+    e = np.zeros(10)
+    L.orc_mt_seq(1234, 0, 10, e.ctypes.data)
+    assert e[:5].tolist() == [2.4835053723904896, 1.516703605376473, 0.6044364871025417, 0.6958665886385867, 1.3065196315496677]
+    assert [float(f"{x:.6g}") for x in e[1:]] == [1.5167, 0.604436, 0.695867, 1.30652, 2.78029, 0.693292, 0.344435, 0.418516, 0.643644]
+    z = np.zeros(2)
+    L.orc_mt_seq(1234, 1, 2, z.ctypes.data)
+    assert abs(z[0] * math.sqrt(0.5) - 0.6133070881429037) < 1e-15 and abs(z[1] * math.sqrt(0.5) + 0.6376291670853887) < 1e-15
+    # bitrand(rng, 10) on a fresh generator: rand!(rng, chunks) first fills the Float64 cache (a zero-length array
+    # fill reserves it), then pops ONE UInt64 from the integer cache; its ten low bits are the BitVector
+    raw = np.empty(2256, dtype=np.uint64)
+    L.orc_mt_raw.argtypes = [C.c_uint64, C.c_void_p, C.c_int64]
+    L.orc_mt_raw(1234, raw.ctypes.data, len(raw))
+    hi500 = int(raw[1002 + 1001]) ^ (((int(raw[1002 + 1252]) | (int(raw[1002 + 1253]) << 64)) << 48) >> 64)
+    assert [(hi500 >> i) & 1 for i in range(10)] == [0, 0, 0, 0, 1, 0, 0, 0, 1, 1]
+    # and the restated cache pops exactly that word first when it is filled from the same doubles
+    u = np.zeros(1, dtype=np.uint64)
+    L.orc_mt_u64.argtypes = [C.c_uint64, C.c_int64, C.c_void_p]
+    L.orc_mt_u64(1234, 1, u.ctypes.data)
+    first_block0 = int(raw[1001]) ^ (((int(raw[1252]) | (int(raw[1253]) << 64)) << 48) >> 64)
+    assert int(u[0]) == first_block0 & 0xFFFFFFFFFFFFFFFF
+
+
 def test_reference_driverlist_is_reproduced_bit_for_bit_from_its_seed(oracle):
     rows = _rows()
     assert len(rows) == 74 and rows[0] == ((1,), 0.2)
