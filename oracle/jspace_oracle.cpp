@@ -936,6 +936,9 @@ void orc_mt_raw(uint64_t mt_seed, uint64_t* out, int64_t n) {
   jmt::MersenneTwister m(mt_seed, v);
   for (int64_t k = 0; k + 1 < n; k += 2) m.ds.next(out + k);
 }
+// Base.hash(::Int64) as restated in julia_mt.hpp (float_form = 0: hash_64_64(x), the form of Julia 1.x for which
+// hash(1) == 0x5bca7c69b794f8ce)
+uint64_t orc_julia_hash(int64_t x, int float_form) { return jmt::julia_hash_int(x, float_form != 0); }
 // slot layout of Set(1:n) under the Variant knobs: out[i] = key in slot i (0 = empty); returns the number of slots
 int64_t orc_intset_layout(int64_t n, const int32_t* variant, int64_t* out, int64_t cap) {
   jmt::Variant v;

@@ -35,7 +35,7 @@ typedef unsigned __int128 u128;
 struct Variant {
   int set_slots = 0;        // slots of Set(1:1000): 0 = follow sizehint!/growth rules (sizehint_mode below), else forced
   int sizehint_mode = 2;    // union!'s sizehint!(s, n): 2 = reserves cld(3n, 2), 1 = reserves n, 0 = no sizehint! call
-  bool hash_float = true;   // hash(::Int64): base/float.jl form (true) or hash_64_64(x) (false)
+  bool hash_float = false;  // hash(::Int64): hash_64_64(x) (false; hash(1) == 0x5bca7c69b794f8ce as the Julia 1.x REPL prints) or the older base/float.jl form (true)
   bool range_fast = true;   // single rand(rng, a:b): SamplerRangeFast (true) or SamplerRangeNDL (false)
   bool set_ndl = true;      // slot draws inside rand(::Set): NDL on UInt64 (true) or Fast on UInt52Raw (false)
   int int_fill_tail = 2;    // doubles taken from the scalar cache at the end of a big array fill

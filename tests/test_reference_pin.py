@@ -121,6 +121,14 @@ def test_mersenne_twister_sequences_of_the_julia_manual(oracle):
     assert int(u[0]) == first_block0 & 0xFFFFFFFFFFFFFFFF
 
 
+def test_julia_integer_hash_known_answer(oracle):
+    # Base.hash(1) as every Julia 1.x REPL prints it (recalled); the slot layout of Set(1:1000) hangs on it
+    L = oracle.lib()
+    L.orc_julia_hash.restype = C.c_uint64
+    L.orc_julia_hash.argtypes = [C.c_int64, C.c_int]
+    assert L.orc_julia_hash(1, 0) == 0x5BCA7C69B794F8CE
+
+
 def test_reference_driverlist_is_reproduced_bit_for_bit_from_its_seed(oracle):
     rows = _rows()
     assert len(rows) == 74 and rows[0] == ((1,), 0.2)
