@@ -121,6 +121,42 @@ def test_mersenne_twister_sequences_of_the_julia_manual(oracle):
     assert int(u[0]) == first_block0 & 0xFFFFFFFFFFFFFFFF
 
 
+def test_masked_rejection_range_draws_of_the_julia_manual(oracle):
+    """`rand(rng, 1:n)` for one draw on a MersenneTwister (SamplerRangeFast) and `shuffle` / `randperm` share one
+    primitive: the low bits of a raw 52-bit draw under a power-of-two mask, redrawn until <= n - 1.  The manual's
+    `shuffle(MersenneTwister(1234), Vector(1:10))` and `randperm(MersenneTwister(1234), 4)` (recalled) pin it."""
+    L = oracle.lib()
+    L.orc_mt_raw.argtypes = [C.c_uint64, C.c_void_p, C.c_int64]
+    raw = np.empty(64, dtype=np.uint64)
+    L.orc_mt_raw(1234, raw.ctypes.data, len(raw))
+    it = iter(int(x) for x in raw)
+
+    def lt(n, mask):
+        while True:
+            x = next(it) & mask
+            if x <= n - 1:
+                return x
+    a = list(range(1, 11))
+    mask = 15
+    for i in range(10, 1, -1):
+        if (mask >> 1) == i:
+            mask >>= 1
+        j = 1 + lt(i, mask)
+        a[i - 1], a[j - 1] = a[j - 1], a[i - 1]
+    assert a == [6, 1, 10, 2, 3, 9, 5, 7, 4, 8]
+    it = iter(int(x) for x in raw)
+    p = [1, 0, 0, 0]
+    mask = 3
+    for i in range(2, 5):
+        j = 1 + lt(i, mask)
+        if i != j:
+            p[i - 1] = p[j - 1]
+        p[j - 1] = i
+        if i == 1 + mask:
+            mask = 2 * mask + 1
+    assert p == [2, 1, 4, 3]
+
+
 def test_julia_integer_hash_known_answer(oracle):
     # Base.hash(1) as every Julia 1.x REPL prints it (recalled); the slot layout of Set(1:1000) hangs on it
     L = oracle.lib()
