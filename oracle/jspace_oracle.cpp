@@ -936,6 +936,12 @@ void orc_mt_raw(uint64_t mt_seed, uint64_t* out, int64_t n) {
   jmt::MersenneTwister m(mt_seed, v);
   for (int64_t k = 0; k + 1 < n; k += 2) m.ds.next(out + k);
 }
+// rand(MersenneTwister(seed), 1:n[k]) for k = 0 .. count-1 from ONE generator (0-based results)
+void orc_mt_range_seq(uint64_t mt_seed, const int64_t* n, int64_t count, int64_t* out) {
+  jmt::Variant v;
+  jmt::MersenneTwister m(mt_seed, v);
+  for (int64_t k = 0; k < count; ++k) out[k] = (int64_t)m.rand_index((uint64_t)n[k]);
+}
 // Base.hash(::Int64) as restated in julia_mt.hpp (float_form = 0: hash_64_64(x), the form of Julia 1.x for which
 // hash(1) == 0x5bca7c69b794f8ce)
 uint64_t orc_julia_hash(int64_t x, int float_form) { return jmt::julia_hash_int(x, float_form != 0); }

@@ -155,6 +155,14 @@ def test_masked_rejection_range_draws_of_the_julia_manual(oracle):
         if i == 1 + mask:
             mask = 2 * mask + 1
     assert p == [2, 1, 4, 3]
+    # the oracle's own rand(seed, 1:n) draws are that primitive (mask = 2^bitlength(n - 1) - 1)
+    ns = np.array([1, 2, 3, 4, 5, 6, 7, 9, 17, 100, 729, 1000, 4097], dtype=np.int64)
+    got = np.zeros(len(ns), dtype=np.int64)
+    L.orc_mt_range_seq.argtypes = [C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p]
+    L.orc_mt_range_seq(1234, ns.ctypes.data, len(ns), got.ctypes.data)
+    it = iter(int(x) for x in raw)
+    want = [lt(int(n), (1 << (int(n) - 1).bit_length()) - 1) for n in ns]
+    assert got.tolist() == want
 
 
 def test_julia_integer_hash_known_answer(oracle):
