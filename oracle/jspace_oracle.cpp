@@ -936,6 +936,22 @@ void orc_mt_raw(uint64_t mt_seed, uint64_t* out, int64_t n) {
   jmt::MersenneTwister m(mt_seed, v);
   for (int64_t k = 0; k + 1 < n; k += 2) m.ds.next(out + k);
 }
+// pinning aid: out[k] = the value randexp() returns when its first raw double is dSFMT output k and the ziggurat
+// accepts at once (NaN otherwise: 1.1 % of the calls)
+void orc_mt_randexp_scan(uint64_t mt_seed, int64_t n, double* out) {
+  jmt::Variant v;
+  jmt::MersenneTwister m(mt_seed, v);
+  const jmt::Zig& z = jmt::MersenneTwister::zig();
+  uint64_t w[2];
+  for (int64_t k = 0; k + 1 < n; k += 2) {
+    m.ds.next(w);
+    for (int h = 0; h < 2; ++h) {
+      const uint64_t ri = w[h] & 0x000fffffffffffffULL;
+      const unsigned idx = (unsigned)(ri & 0xFF);
+      out[k + h] = ri < z.ke[idx] ? (double)ri * z.we[idx] : std::nan("");
+    }
+  }
+}
 // rand(MersenneTwister(seed), 1:n[k]) for k = 0 .. count-1 from ONE generator (0-based results)
 void orc_mt_range_seq(uint64_t mt_seed, const int64_t* n, int64_t count, int64_t* out) {
   jmt::Variant v;
